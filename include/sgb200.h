@@ -1,0 +1,192 @@
+/*
+ * sgb200.h -- C ABI of libsgb200.so, the B200 (sm_100a) implementation of SoftGroup's per-scan
+ * inference hot path (reference: thangvubk/SoftGroup, paths below are relative to its root).
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes, no torch / ATen types.
+ *   - Every pointer named d_* is DEVICE memory; h_* is HOST memory. `stream` is a cudaStream_t
+ *     passed as void*. All work is enqueued on `stream`; functions documented as "blocking"
+ *     synchronise that stream before returning (they return a count the caller needs to size
+ *     the next allocation, exactly where the reference blocks on cudaMemcpy D2H).
+ *   - The library owns no memory between calls. Scratch is caller-provided: ask
+ *     sgb_*_workspace_bytes() and pass a device buffer of at least that size.
+ *   - Return value: >= 0 on success (a count where documented), < 0 = SGB_ERR_*; the message is
+ *     available from sgb_last_error(). Nothing falls back to the CPU.
+ *   - Out-parameter convention follows the reference extension (softgroup/ops/src/softgroup_api.cpp:6-29):
+ *     the caller pre-allocates outputs. Where the reference resize_()s an empty tensor inside the
+ *     callee (voxelize.cpp:29-33, bfs_cluster.cpp:119-122) the C ABI is two-phase:
+ *     *_count (returns sizes) then *_fill.
+ */
+#ifndef SGB200_H
+#define SGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB_OK 0
+#define SGB_ERR_CUDA (-1)      /* a CUDA call failed; see sgb_last_error() */
+#define SGB_ERR_ARG (-2)       /* bad argument (null pointer, negative size, unsupported mode) */
+#define SGB_ERR_WORKSPACE (-3) /* workspace too small */
+#define SGB_ERR_RANGE (-4)     /* input outside the packed-key range (see each function) */
+#define SGB_ERR_OVERFLOW (-5)  /* fixed-capacity structure overflowed */
+
+#define SGB_MAX_NEIGHBORS 1000 /* softgroup/ops/src/bfs_cluster/bfs_cluster.cu:24, octree_ball_query.cu:11 */
+
+const char *sgb_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int sgb_abi_version(void);
+/* 1 if a CUDA device is usable, 0 otherwise (never initialises a context when none exists). */
+int sgb_device_available(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * voxelize_idx -- replaces voxelize_idx_3d (softgroup/ops/src/softgroup_ops.cpp:13-19) =
+ * voxelize_idx<3> / voxelize_inputmap / voxelize_outputmap (voxelize/voxelize.cpp:11-165).
+ * coords: int64 [N, ncol], ncol = 4 (batch,x,y,z) or 3 (x,y,z). Voxel id = first-occurrence rank
+ * in point order; output_map rows are [count, p0, p1, ..., 0-pad] with ascending point index.
+ * mode: 0 unique, 1 first, 2 last, 3 sum, 4 mean (only the map differs; 4 is what the model uses).
+ *
+ * GPU path: keys are packed into 64 bits: batch in [0, 65535], x,y,z in [-32768, 32767]
+ * (all reference configs fit); anything outside returns SGB_ERR_RANGE.
+ *   count (blocking): fills d_input_map [N]; returns M and maxActive through h_M / h_maxActive.
+ *   fill: d_output_coords int64 [M, ncol], d_output_map int32 [M, maxActive+1]. Must be called with
+ *         the SAME workspace contents left by count.
+ * CPU path (host pointers, for DataLoader workers -- softgroup/data/custom.py:239; never touches
+ * CUDA): sgb_voxelize_idx_cpu_begin / _finish with the same semantics and no key-range limit.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_voxelize_idx_workspace_bytes(int N);
+int sgb_voxelize_idx_count(const int64_t *d_coords, int N, int ncol, int mode, int32_t *d_input_map, void *d_ws,
+                           size_t ws_bytes, int *h_M, int *h_maxActive, void *stream);
+int sgb_voxelize_idx_fill(const int64_t *d_coords, int N, int ncol, int mode, int M, int maxActive,
+                          int64_t *d_output_coords, int32_t *d_output_map, void *d_ws, size_t ws_bytes, void *stream);
+void *sgb_voxelize_idx_cpu_begin(const int64_t *h_coords, int N, int ncol, int mode, int32_t *h_input_map, int *h_M,
+                                 int *h_maxActive);
+int sgb_voxelize_idx_cpu_finish(void *handle, const int64_t *h_coords, int64_t *h_output_coords,
+                                int32_t *h_output_map);
+
+/* voxelize_fp / voxelize_bp -- replace voxelize_fp_feat / voxelize_bp_feat (softgroup_ops.cpp:21-38,
+ * voxelize/voxelize.cu:9-62). feats f32 [N,C], rules int32 [M, maxActive+1], out f32 [M,C].
+ * fp overwrites d_out (no pre-zeroing needed); bp ACCUMULATES into d_d_feats like the reference. */
+int sgb_voxelize_fp(const float *d_feats, float *d_out, const int32_t *d_rules, int mode, int M, int maxActive, int C,
+                    void *stream);
+int sgb_voxelize_bp(const float *d_d_out, float *d_d_feats, const int32_t *d_rules, int mode, int M, int maxActive,
+                    int C, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ballquery_batch_p -- replaces ballquery_batch_p_cuda (bfs_cluster/bfs_cluster.cu:68-101, kernel :15-66).
+ * xyz f32 [n,3]; batch_idxs int32 [n]; batch_offsets int32 [B+1] (non-decreasing; query i scans the index
+ * range of its batch). Per point: neighbours with d2 < radius^2 (strict, fp32, d2 evaluated as
+ * fma(dz,dz,fma(dx,dx,dy*dy)) like the compiled reference), ascending point index, self included, first
+ * 1000 kept. d_idx has capacity n*meanActive entries; lists that would cross the capacity are truncated
+ * exactly like the reference (:55-61) and the caller relaunches with a larger meanActive
+ * (softgroup/ops/functions.py:258-266). d_start_len int32 [n,2] = (start, count).
+ * Returns (blocking) the total neighbour count, like the reference's `return cumsum`.
+ * The *_async form leaves the total in d_total (int32 device scalar) and does not synchronise.
+ * B must be <= 1023 and |xyz/radius| < 131072 (SGB_ERR_RANGE otherwise).
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_ballquery_workspace_bytes(int n);
+long long sgb_ballquery_batch_p(int n, int meanActive, float radius, const float *d_xyz, const int32_t *d_batch_idxs,
+                                const int32_t *d_batch_offsets, int B, int32_t *d_idx, int32_t *d_start_len,
+                                void *d_ws, size_t ws_bytes, void *stream);
+int sgb_ballquery_batch_p_async(int n, long long capacity, float radius, const float *d_xyz,
+                                const int32_t *d_batch_idxs, const int32_t *d_batch_offsets, int B, int32_t *d_idx,
+                                int32_t *d_start_len, int32_t *d_total, void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * bfs_cluster -- replaces bfs_cluster / get_clusters / find_cc / fill_cluster_idxs_
+ * (bfs_cluster/bfs_cluster.cpp:33-126), on the GPU, bit-exact including BFS visitation order.
+ * d_ball_query_idxs int32 [nActive], d_start_len int32 [N,2] (DEVICE memory; the reference takes CPU
+ * tensors). threshold semantics (:70-82): a component is kept when (float)size >= thr, where the caller
+ * passes thr = threshold if class_numpoint_mean[class_id] == -1 else threshold * mean.
+ *   count (blocking): returns nCluster, writes sumNPoint to *h_sumNPoint.
+ *   fill: d_cluster_idxs int32 [sumNPoint,2] (cluster id, point idx), d_cluster_offsets int32 [nCluster+1].
+ * Optional per-node segments (d_node_seg int32 [N], d_seg_thr f32 [nSeg]) give every node the threshold of
+ * its segment (used to cluster all classes of a scan in one call); pass NULL for a single threshold.
+ * symmetric_hint != 0 promises that the list graph is symmetric (true for un-capped ball-query lists) and
+ * enables the single-pass union-find labelling; 0 is always exact.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_bfs_cluster_workspace_bytes(int N);
+int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, float thr,
+                          const int32_t *d_node_seg, const float *d_seg_thr, int symmetric_hint, void *d_ws,
+                          size_t ws_bytes, int *h_sumNPoint, void *stream);
+int sgb_bfs_cluster_fill(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, int nCluster,
+                         int sumNPoint, int32_t *d_cluster_idxs, int32_t *d_cluster_offsets, void *d_ws,
+                         size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segment reductions -- replace sec_mean / sec_min / sec_max (sec_mean/sec_mean.cu:13-93) and
+ * global_avg_pool_fp / _bp (roipool/roipool.cu:12-72). inp f32 [S,C]; offsets int32 [nP+1]; out f32 [nP,C].
+ * min/max are exact; mean / avg-pool use a tree reduction (within 1e-5 rel of the sequential sums).
+ * ------------------------------------------------------------------------------------------- */
+int sgb_sec_mean(const float *d_inp, const int32_t *d_offsets, float *d_out, int nProposal, int C, void *stream);
+int sgb_sec_min(const float *d_inp, const int32_t *d_offsets, float *d_out, int nProposal, int C, void *stream);
+int sgb_sec_max(const float *d_inp, const int32_t *d_offsets, float *d_out, int nProposal, int C, void *stream);
+int sgb_global_avg_pool_fp(const float *d_feats, const int32_t *d_offsets, float *d_out, int nProposal, int C,
+                           void *stream);
+int sgb_global_avg_pool_bp(float *d_d_feats, const int32_t *d_offsets, const float *d_d_out, int nProposal, int C,
+                           void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mask IoU / labels -- replace get_mask_iou_on_cluster / get_mask_iou_on_pred / get_mask_label
+ * (cal_iou_and_masklabel/cal_iou_and_masklabel.cu:9-164). Training-side ops of the binding surface.
+ * proposals_idx here is the POINT-INDEX column (int32 [sumNPoint]); instance_labels int64 [N];
+ * d_mask_scores_sigmoid may be NULL (on_cluster). iou f32 [nProposal, nInstance].
+ * ------------------------------------------------------------------------------------------- */
+int sgb_get_mask_iou(const int32_t *d_proposals_idx, const int32_t *d_proposals_offset,
+                     const int64_t *d_instance_labels, const int32_t *d_instance_pointnum,
+                     const float *d_mask_scores_sigmoid, float *d_proposals_iou, int nInstance, int nProposal,
+                     void *stream);
+int sgb_get_mask_label(const int32_t *d_proposals_idx, const int32_t *d_proposals_offset,
+                       const int64_t *d_instance_labels, const int64_t *d_instance_cls,
+                       const float *d_proposals_iou, int nInstance, int nProposal, float iou_thr,
+                       float *d_mask_label, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse convolution -- replaces what the reference delegates to spconv 2.x (call sites
+ * softgroup/model/blocks.py:31-41,50-70,96-129; softgroup/model/softgroup.py:60-65,73-74).
+ * indices int32 [M,4] (b,x,y,z), b in [0,65535], x,y,z in [0,32766].
+ *
+ * Rulebooks ("maps"): int32 [K, Mout]; map[k][j] = input row feeding output row j through kernel offset k,
+ * or -1. Kernel offset order = row-major (k0,k1,k2) like the weight layout [out,k0,k1,k2,in]
+ * (tools/convert_checkpoint.py:17-19).
+ *   subm3:   K=27, Mout=M, map[k][j] = row of indices[j] + (k0-1,k1-1,k2-1)           (SubMConv3d k3 p1)
+ *   down2:   K=8; output voxels = distinct (b, x>>1, y>>1, z>>1) with every coordinate < out_shape
+ *            = floor(shape/2) (inputs on the max plane of an odd dim are dropped), numbered by first
+ *            occurrence in input order. count (blocking) returns Mout; fill writes d_out_indices [Mout,4],
+ *            d_map [8,Mout] (children) and d_inv_map [8,M] (inv_map[k][i] = parent row if input i is child k
+ *            of it, else -1) -- the inverse conv is the same kernel run with inv_map.   (SparseConv3d k2 s2,
+ *            SparseInverseConv3d k2)
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_rulebook_workspace_bytes(int M);
+int sgb_rulebook_subm3(const int32_t *d_indices, int M, int32_t *d_map, void *d_ws, size_t ws_bytes, void *stream);
+int sgb_rulebook_down2_count(const int32_t *d_indices, int M, const int32_t *h_spatial_shape /*[3]*/, void *d_ws,
+                             size_t ws_bytes, void *stream);
+int sgb_rulebook_down2_fill(const int32_t *d_indices, int M, int Mout, int32_t *d_out_indices, int32_t *d_map,
+                            int32_t *d_inv_map, void *d_ws, size_t ws_bytes, void *stream);
+
+/* out[j, out_off + n] = sum_k sum_c act(in[map[k][j], in_off + c]) * W[k][c][n]  (+ residual[j, res_off + n]) (+ bias[n])
+ * act(x) = x                       if d_in_scale == NULL
+ *        = max(x*scale[c]+shift[c], 0)   otherwise (eval-mode BatchNorm1d folded to scale/shift, then ReLU --
+ *          the pre-activation of blocks.py:55-70); absent neighbours contribute exactly 0.
+ * W is f32 [K, Cin, Cout] (the wrapper permutes the reference layout once). d_map == NULL means K == 1 and the
+ * identity map (Custom1x1Subm3d, blocks.py:31-41, and nn.Linear). Row strides are in floats.
+ * fp32 accumulate on CUDA cores (fp32-exact products; see DESIGN.md on why not plain TF32). */
+int sgb_spconv_forward(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
+                       const float *d_W, int Cin, int Cout, const float *d_in_scale, const float *d_in_shift,
+                       const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
+                       int out_stride, int out_off, void *stream);
+
+/* y[i, c] = max(x[i, c]*scale[c] + shift[c], 0) (relu != 0) -- BatchNorm1d(eval)+ReLU over rows. */
+int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const float *d_shift, int relu, float *d_y,
+                int y_stride, int M, int C, void *stream);
+
+/* out[i, :] = in[index[i], :]  (the "devoxelize" gather of softgroup.py:374); index int32 [N]. */
+int sgb_gather_rows(const float *d_in, const int32_t *d_index, float *d_out, int N, int C, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB200_H */

@@ -1,0 +1,346 @@
+// ballquery.cu -- ballquery_batch_p on a uniform-grid hash.
+//
+// Replaces the O(n * n_b) brute force of softgroup/ops/src/bfs_cluster/bfs_cluster.cu:15-66 with
+//   (1) cell hash:   cell = floor(p / h), h = radius*(1+1e-4) in fp64; 64-bit key (segment, cx, cy, cz) ->
+//                    open-addressing hash (atomicCAS); counts per cell; exclusive scan; scatter of
+//                    (x,y,z,idx) records so every cell is one contiguous run of 16-byte records;
+//   (2) query:       one CTA per occupied cell. The <=27 neighbouring runs are staged in shared memory
+//                    and bitonic-sorted by point index ONCE per cell; each query of the cell (one warp) then
+//                    streams the staged candidates in index order -> ballot/popc compaction gives the
+//                    ascending list directly and the "first 1000 by index" cap (:43-48) is a loop exit.
+// Exactness: the distance is evaluated with the reference's compiled contraction order
+//   d2 = fma(dz,dz, fma(dx,dx, dy*dy)),  hit iff d2 < radius*radius   (strict, fp32)
+// and any pair with d2 < r^2 differs by < h in every coordinate, so it lies in the 27-cell stencil.
+// List placement uses an atomic cursor like the reference (:52) -- per-point lists are deterministic,
+// the global layout is not.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sgb {
+
+constexpr int kBqThreads = 256;
+constexpr int kBqWarps = kBqThreads / 32;
+constexpr int kBqSMax = 4096;  // staged candidates per cell (16 B each)
+constexpr int kCellBias = 131072;
+constexpr int kMaxSeg = 1023;
+
+struct BqWs {
+  unsigned long long *keys;  // [cap]
+  int32_t *slot_cnt;         // [cap]
+  int32_t *slot_start;       // [cap]
+  int32_t *slot_fill;        // [cap]
+  int32_t *cell_slot;        // [n] cell id -> slot
+  int32_t *cell_cnt;         // [n] -> scanned in place to starts
+  int32_t *slot_of;          // [n]
+  float4 *sorted;            // [n] (x,y,z,idx)
+  int32_t *scalars;          // 0: ncells, 1: work counter, 2: error flag, 3: total
+  int32_t *scan_tmp;
+  uint32_t cap;
+};
+
+static size_t bq_cap(int n) { return pow2_at_least((size_t)std::max(n, 1) * 2); }
+
+static bool bq_carve(void *ws, size_t bytes, int n, BqWs &w) {
+  Arena a(ws, bytes);
+  w.cap = (uint32_t)bq_cap(n);
+  w.scalars = a.take<int32_t>(64);
+  w.keys = a.take<unsigned long long>(w.cap);
+  w.slot_cnt = a.take<int32_t>(w.cap);
+  w.slot_start = a.take<int32_t>(w.cap);
+  w.slot_fill = a.take<int32_t>(w.cap);
+  w.cell_slot = a.take<int32_t>((size_t)n + 1);
+  w.cell_cnt = a.take<int32_t>((size_t)n + 1);
+  w.slot_of = a.take<int32_t>((size_t)n + 1);
+  w.sorted = a.take<float4>((size_t)n + 1);
+  w.scan_tmp = a.take<int32_t>(scan_temp_elems((size_t)n + 1));
+  return w.scan_tmp != nullptr;
+}
+
+__device__ __forceinline__ unsigned long long cell_key(int seg, int cx, int cy, int cz) {
+  return ((unsigned long long)seg << 54) | ((unsigned long long)(cx + kCellBias) << 36) |
+         ((unsigned long long)(cy + kCellBias) << 18) | (unsigned long long)(cz + kCellBias);
+}
+
+__global__ void bq_insert_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ batch_idxs, int n,
+                                 double inv_h, BqWs w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double fx = floor((double)xyz[3 * (size_t)i] * inv_h);
+  double fy = floor((double)xyz[3 * (size_t)i + 1] * inv_h);
+  double fz = floor((double)xyz[3 * (size_t)i + 2] * inv_h);
+  int seg = batch_idxs[i];
+  const double lim = (double)(kCellBias - 2);
+  if (!(fabs(fx) < lim && fabs(fy) < lim && fabs(fz) < lim) || seg < 0 || seg > kMaxSeg) {
+    w.scalars[2] = 1;
+    w.slot_of[i] = -1;
+    return;
+  }
+  unsigned long long key = cell_key(seg, (int)fx, (int)fy, (int)fz);
+  uint32_t mask = w.cap - 1;
+  uint32_t s = hash64(key) & mask;
+  while (true) {
+    unsigned long long cur = w.keys[s];
+    if (cur == key) break;
+    if (cur == kEmptyKey) {
+      unsigned long long old = atomicCAS(&w.keys[s], kEmptyKey, key);
+      if (old == kEmptyKey) {
+        int id = atomicAdd(&w.scalars[0], 1);
+        w.cell_slot[id] = (int32_t)s;
+        break;
+      }
+      if (old == key) break;
+    }
+    s = (s + 1) & mask;
+  }
+  w.slot_of[i] = (int32_t)s;
+  atomicAdd(&w.slot_cnt[s], 1);
+}
+
+__global__ void bq_cellcnt_kernel(int n, BqWs w) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  w.cell_cnt[c] = (c < w.scalars[0]) ? w.slot_cnt[w.cell_slot[c]] : 0;
+}
+
+__global__ void bq_cellstart_kernel(int n, BqWs w) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= w.scalars[0]) return;
+  w.slot_start[w.cell_slot[c]] = w.cell_cnt[c];
+}
+
+__global__ void bq_scatter_kernel(const float *__restrict__ xyz, int n, BqWs w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = w.slot_of[i];
+  if (s < 0) return;
+  int pos = w.slot_start[s] + atomicAdd(&w.slot_fill[s], 1);
+  w.sorted[pos] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __int_as_float(i));
+}
+
+__device__ __forceinline__ bool bq_hit(float qx, float qy, float qz, float x, float y, float z, float r2) {
+  float dx = __fsub_rn(qx, x), dy = __fsub_rn(qy, y), dz = __fsub_rn(qz, z);
+  float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+  return d2 < r2;
+}
+
+// Emit one query's list: staged hits (ascending) -> global, reference truncation rules (bfs_cluster.cu:52-65).
+__device__ __forceinline__ void bq_emit(int qi, int cnt, const int32_t *stage, int32_t *__restrict__ idx,
+                                        int32_t *__restrict__ start_len, int32_t *total, long long capacity, int lane) {
+  int base = 0;
+  if (lane == 0) {
+    base = atomicAdd(total, cnt);
+    start_len[2 * (size_t)qi] = base;
+    start_len[2 * (size_t)qi + 1] = cnt;
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if ((long long)base >= capacity) return;
+  int cw = cnt;
+  if ((long long)base + cnt >= capacity) cw = (int)(capacity - base);
+  for (int k = lane; k < cw; k += 32) idx[(size_t)base + k] = stage[k];
+}
+
+__global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__restrict__ xyz,
+                                                              const int32_t *__restrict__ batch_idxs,
+                                                              const int32_t *__restrict__ batch_offsets, int n,
+                                                              float radius, long long capacity,
+                                                              int32_t *__restrict__ idx,
+                                                              int32_t *__restrict__ start_len, BqWs w) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *S = reinterpret_cast<float4 *>(smem_raw);                                   // [kBqSMax]
+  int32_t *stage = reinterpret_cast<int32_t *>(smem_raw + sizeof(float4) * kBqSMax);  // [kBqWarps][1000]
+  __shared__ int nb_start[27], nb_cnt[27], nb_off[28];
+  __shared__ int s_cell;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float r2 = __fmul_rn(radius, radius);
+  const int ncells = w.scalars[0];
+  int32_t *my_stage = stage + warp * SGB_MAX_NEIGHBORS;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_cell = atomicAdd(&w.scalars[1], 1);
+    __syncthreads();
+    const int cell = s_cell;
+    if (cell >= ncells) break;
+    const int cslot = w.cell_slot[cell];
+    const unsigned long long ckey = w.keys[cslot];
+    if (tid < 27) {
+      int seg = (int)(ckey >> 54);
+      int cx = (int)((ckey >> 36) & 0x3FFFF) + (tid % 3) - 1;
+      int cy = (int)((ckey >> 18) & 0x3FFFF) + ((tid / 3) % 3) - 1;
+      int cz = (int)(ckey & 0x3FFFF) + (tid / 9) - 1;
+      int st = 0, ct = 0;
+      if (cx >= 0 && cy >= 0 && cz >= 0 && cx < 2 * kCellBias && cy < 2 * kCellBias && cz < 2 * kCellBias) {
+        unsigned long long key = ((unsigned long long)seg << 54) | ((unsigned long long)cx << 36) |
+                                 ((unsigned long long)cy << 18) | (unsigned long long)cz;
+        uint32_t s = hash_find(w.keys, w.cap - 1, key);
+        if (s != 0xFFFFFFFFu) { st = w.slot_start[s]; ct = w.slot_cnt[s]; }
+      }
+      nb_start[tid] = st;
+      nb_cnt[tid] = ct;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0;
+      for (int k = 0; k < 27; k++) { nb_off[k] = acc; acc += nb_cnt[k]; }
+      nb_off[27] = acc;
+    }
+    __syncthreads();
+    const int total_s = nb_off[27];
+    const int q_start = w.slot_start[cslot], q_cnt = w.slot_cnt[cslot];
+
+    if (total_s <= kBqSMax) {
+      // ---- stage the stencil, sort by point index ------------------------------------------------
+      int P = 32;
+      while (P < total_s) P <<= 1;
+      for (int k = 0; k < 27; k++) {
+        int c = nb_cnt[k], st = nb_start[k], o = nb_off[k];
+        for (int t = tid; t < c; t += kBqThreads) S[o + t] = w.sorted[st + t];
+      }
+      for (int t = total_s + tid; t < P; t += kBqThreads) S[t] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+      __syncthreads();
+      for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = tid; t < P; t += kBqThreads) {
+            int u = t ^ j;
+            if (u > t) {
+              float4 a = S[t], b = S[u];
+              bool asc = ((t & k) == 0);
+              bool gt = __float_as_int(a.w) > __float_as_int(b.w);
+              if (gt == asc) { S[t] = b; S[u] = a; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      // ---- queries of this cell: one warp each ----------------------------------------------------
+      for (int q = warp; q < q_cnt; q += kBqWarps) {
+        float4 qp = w.sorted[q_start + q];
+        int qi = __float_as_int(qp.w);
+        int cnt = 0;
+        for (int b0 = 0; b0 < total_s && cnt < SGB_MAX_NEIGHBORS; b0 += 32) {
+          int t = b0 + lane;
+          bool hit = false;
+          int ci = 0;
+          if (t < total_s) {
+            float4 c = S[t];
+            ci = __float_as_int(c.w);
+            hit = bq_hit(qp.x, qp.y, qp.z, c.x, c.y, c.z, r2);
+          }
+          unsigned m = __ballot_sync(0xffffffffu, hit);
+          int pos = cnt + __popc(m & ((1u << lane) - 1));
+          if (hit && pos < SGB_MAX_NEIGHBORS) my_stage[pos] = ci;
+          cnt = min(cnt + __popc(m), SGB_MAX_NEIGHBORS);
+        }
+        __syncwarp();
+        bq_emit(qi, cnt, my_stage, idx, start_len, &w.scalars[3], capacity, lane);
+        __syncwarp();
+      }
+    } else {
+      // ---- oversize stencil (> kBqSMax candidates): exact index-order scan of the segment ---------
+      for (int q = warp; q < q_cnt; q += kBqWarps) {
+        float4 qp = w.sorted[q_start + q];
+        int qi = __float_as_int(qp.w);
+        int b = batch_idxs[qi];
+        int s0 = batch_offsets[b], e0 = batch_offsets[b + 1];
+        int cnt = 0;
+        for (int b0 = s0; b0 < e0 && cnt < SGB_MAX_NEIGHBORS; b0 += 32) {
+          int t = b0 + lane;
+          bool hit = false;
+          if (t < e0) hit = bq_hit(qp.x, qp.y, qp.z, xyz[3 * (size_t)t], xyz[3 * (size_t)t + 1], xyz[3 * (size_t)t + 2], r2);
+          unsigned m = __ballot_sync(0xffffffffu, hit);
+          int pos = cnt + __popc(m & ((1u << lane) - 1));
+          if (hit && pos < SGB_MAX_NEIGHBORS) my_stage[pos] = t;
+          cnt = min(cnt + __popc(m), SGB_MAX_NEIGHBORS);
+        }
+        __syncwarp();
+        bq_emit(qi, cnt, my_stage, idx, start_len, &w.scalars[3], capacity, lane);
+        __syncwarp();
+      }
+    }
+  }
+}
+
+static int bq_launch(int n, long long capacity, float radius, const float *xyz, const int32_t *batch_idxs,
+                     const int32_t *batch_offsets, int B, int32_t *idx, int32_t *start_len, void *ws, size_t ws_bytes,
+                     cudaStream_t st, BqWs &w) {
+  SGB_REQUIRE(n >= 0 && B >= 1 && B <= kMaxSeg && radius > 0.f, SGB_ERR_ARG, "ballquery arguments");
+  SGB_REQUIRE(xyz && batch_idxs && batch_offsets && start_len && ws, SGB_ERR_ARG, "null pointer");
+  SGB_REQUIRE(bq_carve(ws, ws_bytes, n, w), SGB_ERR_WORKSPACE, "ballquery workspace too small");
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.keys, 0xFF, (size_t)w.cap * 8, st));
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.slot_cnt, 0, (size_t)w.cap * 4, st));
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.slot_fill, 0, (size_t)w.cap * 4, st));
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 64 * 4, st));
+  double h = (double)radius * (1.0 + 1e-4);
+  int nb = div_up(n, 256);
+  bq_insert_kernel<<<nb, 256, 0, st>>>(xyz, batch_idxs, n, 1.0 / h, w);
+  SGB_LAUNCH_CHECK();
+  bq_cellcnt_kernel<<<nb, 256, 0, st>>>(n, w);
+  SGB_LAUNCH_CHECK();
+  int rc = exclusive_scan_i32(w.cell_cnt, w.cell_cnt, (size_t)n, nullptr, w.scan_tmp, st);
+  if (rc) return rc;
+  bq_cellstart_kernel<<<nb, 256, 0, st>>>(n, w);
+  SGB_LAUNCH_CHECK();
+  bq_scatter_kernel<<<nb, 256, 0, st>>>(xyz, n, w);
+  SGB_LAUNCH_CHECK();
+  size_t smem = sizeof(float4) * kBqSMax + sizeof(int32_t) * kBqWarps * SGB_MAX_NEIGHBORS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(bq_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int grid = std::min(std::max(n, 1), kNumSMs * 2);
+  bq_query_kernel<<<grid, kBqThreads, smem, st>>>(xyz, batch_idxs, batch_offsets, n, radius, capacity, idx, start_len, w);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" {
+
+size_t sgb_ballquery_workspace_bytes(int n) {
+  if (n < 0) n = 0;
+  size_t cap = bq_cap(n);
+  size_t b = align_up(64 * 4) + align_up(cap * 8) + 3 * align_up(cap * 4) + 3 * align_up(((size_t)n + 1) * 4) +
+             align_up(((size_t)n + 1) * 16) + align_up(scan_temp_elems((size_t)n + 1) * 4);
+  return b + 1024;
+}
+
+int sgb_ballquery_batch_p_async(int n, long long capacity, float radius, const float *d_xyz,
+                                const int32_t *d_batch_idxs, const int32_t *d_batch_offsets, int B, int32_t *d_idx,
+                                int32_t *d_start_len, int32_t *d_total, void *d_ws, size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    if (d_total) SGB_CUDA_CHECK(cudaMemsetAsync(d_total, 0, 4, st));
+    return SGB_OK;
+  }
+  SGB_REQUIRE(capacity == 0 || d_idx, SGB_ERR_ARG, "null idx");
+  BqWs w;
+  int rc = bq_launch(n, capacity, radius, d_xyz, d_batch_idxs, d_batch_offsets, B, d_idx, d_start_len, d_ws, ws_bytes,
+                     st, w);
+  if (rc) return rc;
+  if (d_total) SGB_CUDA_CHECK(cudaMemcpyAsync(d_total, &w.scalars[3], 4, cudaMemcpyDeviceToDevice, st));
+  return SGB_OK;
+}
+
+long long sgb_ballquery_batch_p(int n, int meanActive, float radius, const float *d_xyz, const int32_t *d_batch_idxs,
+                                const int32_t *d_batch_offsets, int B, int32_t *d_idx, int32_t *d_start_len,
+                                void *d_ws, size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return 0;
+  SGB_REQUIRE(meanActive >= 0, SGB_ERR_ARG, "meanActive");
+  BqWs w;
+  int rc = bq_launch(n, (long long)n * meanActive, radius, d_xyz, d_batch_idxs, d_batch_offsets, B, d_idx,
+                     d_start_len, d_ws, ws_bytes, st, w);
+  if (rc) return rc;
+  int h[4];
+  SGB_CUDA_CHECK(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+  SGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  SGB_REQUIRE(h[2] == 0, SGB_ERR_RANGE, "ballquery: |xyz/radius| >= 131070 or batch index outside [0,1023]");
+  return (long long)h[3];
+}
+}

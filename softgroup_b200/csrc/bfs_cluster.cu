@@ -1,0 +1,304 @@
+// bfs_cluster.cu -- soft-grouping clustering on the GPU, bit-exact with the reference's sequential BFS
+// (softgroup/ops/src/bfs_cluster/bfs_cluster.cpp:33-126).
+//
+// The reference visits i = 0..N-1, starts a std::queue BFS from every unvisited i over the DIRECTED list graph
+// and keeps components with (int)size >= thr; cluster_idxs is in BFS visitation order, clusters in seed order.
+// Parallel restatement (validated against the compiled reference in tests/):
+//   (1) label[v] = min index among all nodes that can reach v (v included). That node is exactly the seed whose
+//       BFS claims v: it has no smaller ancestor, so it is unvisited when the outer loop reaches it, and no node on
+//       its path to v can have been claimed earlier. Computed by min-propagation along directed edges with pointer
+//       jumping (label[label[v]] is again an ancestor) until a pass changes nothing.
+//   (2) sizes per label (warp-aggregated atomics) -> threshold -> one packed int64 exclusive scan gives every kept
+//       seed its cluster id (rank among kept seeds = ascending seed order) and its output offset.
+//   (3) one CTA per kept cluster replays the BFS level-synchronously. Queue order is reproduced with a 64-bit
+//       atomicMin key per node: key[v] = min over parents u listing v of (queue position of u, slot of v in u's
+//       list). The winning parent is the first discoverer; children of one parent keep list order; parents keep
+//       queue order -> next level = concatenation over parents (in queue order) of their won children (in list
+//       order), placed with a block scan of per-parent win counts. No sort is needed.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sgb {
+
+struct BfsWs {
+  int32_t *label;      // [N]
+  int32_t *size;       // [N] component size at the seed
+  long long *packed;   // [N] keep ? (1<<32 | size) : 0  -> exclusive scan
+  unsigned long long *key;  // [N]
+  int32_t *root_of;    // [N] cluster id -> seed
+  int32_t *wins;       // [N] per queue position
+  int32_t *scalars;    // 0: changed flag, 1..: spare
+  long long *totals;   // [1] packed total
+  long long *scan_tmp;
+};
+
+static bool bfs_carve(void *ws, size_t bytes, int N, BfsWs &w) {
+  Arena a(ws, bytes);
+  size_t n1 = (size_t)N + 1;
+  w.scalars = a.take<int32_t>(64);
+  w.totals = a.take<long long>(8);
+  w.label = a.take<int32_t>(n1);
+  w.size = a.take<int32_t>(n1);
+  w.packed = a.take<long long>(n1);
+  w.key = a.take<unsigned long long>(n1);
+  w.root_of = a.take<int32_t>(n1);
+  w.wins = a.take<int32_t>(n1);
+  w.scan_tmp = a.take<long long>(scan_temp_elems(n1));
+  return w.scan_tmp != nullptr;
+}
+
+__global__ void bfs_init_kernel(int N, BfsWs w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  w.label[v] = v;
+  w.size[v] = 0;
+}
+
+// one warp per source node; pushes the (chased) label of u to every listed v
+__global__ void bfs_propagate_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len, int N,
+                                     BfsWs w) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  volatile int32_t *label = w.label;
+  bool changed = false;
+  for (int u = warp; u < N; u += nwarps) {
+    int lu = label[u];
+    while (true) {  // pointer jumping: an ancestor's label is an ancestor too
+      int l2 = label[lu];
+      if (l2 >= lu) break;
+      lu = l2;
+    }
+    if (lane == 0 && lu < label[u]) atomicMin(&w.label[u], lu);
+    int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+    for (int j = lane; j < l; j += 32) {
+      int v = __ldg(&idxs[(size_t)s + j]);
+      if (label[v] > lu) {
+        int old = atomicMin(&w.label[v], lu);
+        changed |= (old > lu);
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, changed) && lane == 0) w.scalars[0] = 1;
+}
+
+__global__ void bfs_size_kernel(int N, BfsWs w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = v < N;
+  int l = active ? w.label[v] : -1;
+  unsigned am = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  unsigned peers = __match_any_sync(am, l);
+  int leader = __ffs(peers) - 1;
+  if ((threadIdx.x & 31) == leader) atomicAdd(&w.size[l], __popc(peers));
+}
+
+__global__ void bfs_pack_kernel(int N, float thr, const int32_t *__restrict__ node_seg,
+                                const float *__restrict__ seg_thr, BfsWs w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  long long p = 0;
+  if (w.label[v] == v) {
+    float t = node_seg ? seg_thr[node_seg[v]] : thr;
+    int sz = w.size[v];
+    if ((float)sz >= t) p = (1ll << 32) | (long long)sz;  // `(int)CC.pt_idxs.size() >= thr` (bfs_cluster.cpp:78)
+  }
+  w.packed[v] = p;
+}
+
+__global__ void bfs_roots_kernel(int N, int nCluster, int sumNPoint, int32_t *__restrict__ cluster_offsets, BfsWs w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v == 0) cluster_offsets[nCluster] = sumNPoint;
+  if (v >= N) return;
+  if (w.label[v] == v) {
+    long long p = w.packed[v];
+    // a seed is kept iff the exclusive prefix grows by one cluster after it
+    long long nxt = (v + 1 < N) ? w.packed[v + 1] : w.totals[0];
+    if ((nxt - p) >> 32) {
+      int c = (int)(p >> 32);
+      w.root_of[c] = v;
+      cluster_offsets[c] = (int)(p & 0xFFFFFFFFll);
+    }
+  }
+}
+
+constexpr int kEmitThreads = 256;
+
+__global__ void __launch_bounds__(kEmitThreads) bfs_emit_kernel(const int32_t *__restrict__ idxs,
+                                                                const int32_t *__restrict__ start_len,
+                                                                const int32_t *__restrict__ cluster_offsets,
+                                                                int32_t *__restrict__ cluster_idxs, BfsWs w) {
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = kEmitThreads / 32;
+  const int seed = w.root_of[c];
+  const int base = cluster_offsets[c];
+  int32_t *order = cluster_idxs + 2 * (size_t)base;  // order[2*p+1] = p-th visited node
+  int32_t *wins = w.wins + base;
+  __shared__ int s_warp[nwarps];
+  __shared__ int s_carry, s_total;
+
+  if (tid == 0) {
+    w.key[seed] = 0ull;
+    order[0] = c;
+    order[1] = seed;
+  }
+  __syncthreads();
+  int a = 0, b = 1;
+  while (true) {
+    // ---- A: claim ------------------------------------------------------------------------------
+    for (int p = a + warp; p < b; p += nwarps) {
+      int u = __ldcg(&order[2 * (size_t)p + 1]);
+      int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+      unsigned long long hi = (unsigned long long)(p + 1) << 32;
+      for (int j = lane; j < l; j += 32) {
+        int v = __ldg(&idxs[(size_t)s + j]);
+        if (__ldg(&w.label[v]) == seed) atomicMin(&w.key[v], hi | (unsigned)j);
+      }
+    }
+    __syncthreads();
+    // ---- B: count wins per parent --------------------------------------------------------------
+    for (int p = a + warp; p < b; p += nwarps) {
+      int u = __ldcg(&order[2 * (size_t)p + 1]);
+      int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+      unsigned long long hi = (unsigned long long)(p + 1) << 32;
+      int cnt = 0;
+      for (int j0 = 0; j0 < l; j0 += 32) {
+        int j = j0 + lane;
+        bool win = false;
+        if (j < l) {
+          int v = __ldg(&idxs[(size_t)s + j]);
+          win = (__ldcg(&w.key[v]) == (hi | (unsigned)j));
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, win));
+      }
+      if (lane == 0) wins[p] = cnt;
+    }
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    // ---- exclusive scan of wins[a..b) ----------------------------------------------------------
+    for (int p0 = a; p0 < b; p0 += kEmitThreads) {
+      int p = p0 + tid;
+      int x = (p < b) ? __ldcg(&wins[p]) : 0;
+      int inc = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      int woff = 0;
+      for (int k = 0; k < warp; k++) woff += s_warp[k];
+      int carry = s_carry;
+      if (p < b) wins[p] = carry + woff + inc - x;
+      __syncthreads();
+      if (tid == kEmitThreads - 1) s_carry = carry + woff + inc;
+      __syncthreads();
+    }
+    if (tid == 0) s_total = s_carry;
+    __syncthreads();
+    const int total = s_total;
+    if (total == 0) break;
+    // ---- C: write won children in (parent queue order, list order) ------------------------------
+    for (int p = a + warp; p < b; p += nwarps) {
+      int u = __ldcg(&order[2 * (size_t)p + 1]);
+      int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+      unsigned long long hi = (unsigned long long)(p + 1) << 32;
+      int run = b + __ldcg(&wins[p]);
+      for (int j0 = 0; j0 < l; j0 += 32) {
+        int j = j0 + lane;
+        bool win = false;
+        int v = 0;
+        if (j < l) {
+          v = __ldg(&idxs[(size_t)s + j]);
+          win = (__ldcg(&w.key[v]) == (hi | (unsigned)j));
+        }
+        unsigned m = __ballot_sync(0xffffffffu, win);
+        if (win) {
+          int pos = run + __popc(m & ((1u << lane) - 1));
+          order[2 * (size_t)pos] = c;
+          order[2 * (size_t)pos + 1] = v;
+        }
+        run += __popc(m);
+      }
+    }
+    __syncthreads();
+    a = b;
+    b += total;
+  }
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" {
+
+size_t sgb_bfs_cluster_workspace_bytes(int N) {
+  if (N < 0) N = 0;
+  size_t n1 = (size_t)N + 1;
+  size_t b = align_up(64 * 4) + align_up(64) + 4 * align_up(n1 * 4) + 2 * align_up(n1 * 8) +
+             align_up(scan_temp_elems(n1) * 8);
+  return b + 1024;
+}
+
+int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, float thr,
+                          const int32_t *d_node_seg, const float *d_seg_thr, int symmetric_hint, void *d_ws,
+                          size_t ws_bytes, int *h_sumNPoint, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  (void)symmetric_hint;
+  SGB_REQUIRE(N >= 0 && h_sumNPoint, SGB_ERR_ARG, "bfs_cluster arguments");
+  if (N == 0) { *h_sumNPoint = 0; return 0; }
+  SGB_REQUIRE(d_start_len && d_ws, SGB_ERR_ARG, "null pointer");
+  SGB_REQUIRE((d_node_seg == nullptr) == (d_seg_thr == nullptr), SGB_ERR_ARG, "node_seg / seg_thr must come together");
+  BfsWs w;
+  SGB_REQUIRE(bfs_carve(d_ws, ws_bytes, N, w), SGB_ERR_WORKSPACE, "bfs_cluster workspace too small");
+  int nb = div_up(N, 256);
+  bfs_init_kernel<<<nb, 256, 0, st>>>(N, w);
+  SGB_LAUNCH_CHECK();
+  int grid = std::min(div_up((long long)N * 32, 256), kNumSMs * 16);
+  for (int it = 0; it < 100000; it++) {
+    SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 4, st));
+    bfs_propagate_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w);
+    SGB_LAUNCH_CHECK();
+    int changed = 0;
+    SGB_CUDA_CHECK(cudaMemcpyAsync(&changed, w.scalars, 4, cudaMemcpyDeviceToHost, st));
+    SGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!changed) break;
+  }
+  bfs_size_kernel<<<nb, 256, 0, st>>>(N, w);
+  SGB_LAUNCH_CHECK();
+  bfs_pack_kernel<<<nb, 256, 0, st>>>(N, thr, d_node_seg, d_seg_thr, w);
+  SGB_LAUNCH_CHECK();
+  int rc = exclusive_scan_i64(w.packed, w.packed, (size_t)N, w.totals, w.scan_tmp, st);
+  if (rc) return rc;
+  long long tot = 0;
+  SGB_CUDA_CHECK(cudaMemcpyAsync(&tot, w.totals, 8, cudaMemcpyDeviceToHost, st));
+  SGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  *h_sumNPoint = (int)(tot & 0xFFFFFFFFll);
+  return (int)(tot >> 32);
+}
+
+int sgb_bfs_cluster_fill(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, int nCluster,
+                         int sumNPoint, int32_t *d_cluster_idxs, int32_t *d_cluster_offsets, void *d_ws,
+                         size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SGB_REQUIRE(N >= 0 && nCluster >= 0 && sumNPoint >= 0 && d_cluster_offsets, SGB_ERR_ARG, "bfs_cluster_fill arguments");
+  if (N == 0 || nCluster == 0) {
+    SGB_CUDA_CHECK(cudaMemsetAsync(d_cluster_offsets, 0, 4, st));
+    return SGB_OK;
+  }
+  SGB_REQUIRE(d_start_len && d_cluster_idxs && d_ws, SGB_ERR_ARG, "null pointer");
+  BfsWs w;
+  SGB_REQUIRE(bfs_carve(d_ws, ws_bytes, N, w), SGB_ERR_WORKSPACE, "bfs_cluster workspace too small");
+  bfs_roots_kernel<<<div_up(N, 256), 256, 0, st>>>(N, nCluster, sumNPoint, d_cluster_offsets, w);
+  SGB_LAUNCH_CHECK();
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.key, 0xFF, (size_t)N * 8, st));
+  bfs_emit_kernel<<<nCluster, kEmitThreads, 0, st>>>(d_ball_query_idxs, d_start_len, d_cluster_offsets,
+                                                     d_cluster_idxs, w);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+}

@@ -1,0 +1,369 @@
+"""softgroup_b200.ops.functions -- the reference's `softgroup.ops` binding surface on libsgb200.so.
+
+Same names, argument meaning and return layout as softgroup/ops/functions.py of the reference
+(thangvubk/SoftGroup): ball_query, ballquery_batch_p, bfs_cluster, voxelization_idx, voxelization,
+global_avg_pool, sec_mean/min/max, get_mask_iou_on_cluster, get_mask_iou_on_pred, get_mask_label.
+Every op runs in hand-written sm_100a CUDA behind the C ABI of include/sgb200.h; nothing here computes
+on the CPU except `voxelization_idx` on CPU tensors (the reference runs it inside DataLoader workers,
+softgroup/data/custom.py:239) which calls the library's C++ host path.
+
+Differences that are extensions, not changes:
+  * voxelization_idx and bfs_cluster also accept CUDA tensors and then return CUDA tensors
+    (the reference only takes CPU tensors there); CPU inputs to bfs_cluster are computed on the GPU and
+    returned on the CPU, like `.new()` on the inputs did in the reference (functions.py:295-296).
+  * ballquery_batch_p lays the per-point lists out through an atomic cursor exactly like the reference,
+    so only `idx[start:start+len]` per point is meaningful (it always was).
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def _cuda(t):
+    return t if t.is_cuda else t.cuda()
+
+
+# ----------------------------------------------------------------------------------------------
+# ball query
+# ----------------------------------------------------------------------------------------------
+def ball_query(coords, batch_idxs, batch_offsets, radius, mean_active, with_octree=False):
+    """functions.py:7-11 of the reference."""
+    if with_octree:
+        return octree_ball_query(coords, mean_active, radius)
+    return ballquery_batch_p(coords, batch_idxs, batch_offsets, radius, mean_active)
+
+
+def octree_ball_query(coords, mean_active, radius):
+    """functions.py:14-44 of the reference (SoftGroup++). Not built yet: fail loudly, never fall back."""
+    raise NotImplementedError('octree_ball_query is scheduled after the SoftGroup (non ++) path; see DESIGN.md')
+
+
+class BallQueryBatchP(Function):
+    """functions.py:237-275."""
+
+    @staticmethod
+    def forward(ctx, coords, batch_idxs, batch_offsets, radius, meanActive):
+        n = coords.size(0)
+        assert coords.is_contiguous() and coords.is_cuda
+        assert batch_idxs.is_contiguous() and batch_idxs.is_cuda
+        assert batch_offsets.is_contiguous() and batch_offsets.is_cuda
+        L = _lib.lib()
+        dev = coords.device
+        B = batch_offsets.numel() - 1
+        start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        if n == 0:
+            return torch.empty(0, dtype=torch.int32, device=dev), start_len
+        ws = _ws(L.sgb_ballquery_workspace_bytes(n), dev)
+        meanActive = int(meanActive)
+        while True:
+            idx = torch.empty(max(n * meanActive, 1), dtype=torch.int32, device=dev)
+            nActive = check(
+                L.sgb_ballquery_batch_p(n, meanActive, float(radius), ptr(coords), ptr(batch_idxs), ptr(batch_offsets),
+                                        B, ptr(idx), ptr(start_len), ptr(ws), ws.numel(), _stream()),
+                'sgb_ballquery_batch_p')
+            if nActive <= n * meanActive:
+                break
+            meanActive = int(nActive // n + 1)
+        return idx[:nActive], start_len
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None, None, None, None
+
+
+ballquery_batch_p = BallQueryBatchP.apply
+
+
+# ----------------------------------------------------------------------------------------------
+# clustering
+# ----------------------------------------------------------------------------------------------
+def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, symmetric=False):
+    """GPU clustering on device tensors. thr: float threshold on the component size (already multiplied by the
+    class mean when that applies). Optional per-node segment thresholds. Returns CUDA tensors
+    (cluster_idxs int32 [sumNPoint,2], cluster_offsets int32 [nCluster+1])."""
+    L = _lib.lib()
+    dev = start_len.device
+    N = start_len.size(0)
+    ws = _ws(L.sgb_bfs_cluster_workspace_bytes(N), dev)
+    s = ctypes.c_int(0)
+    nC = check(
+        L.sgb_bfs_cluster_count(ptr(ball_query_idxs), ptr(start_len), N, float(thr), ptr(node_seg), ptr(seg_thr),
+                                int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), _stream()),
+        'sgb_bfs_cluster_count')
+    cluster_idxs = torch.empty((s.value, 2), dtype=torch.int32, device=dev)
+    cluster_offsets = torch.empty(nC + 1, dtype=torch.int32, device=dev)
+    check(
+        L.sgb_bfs_cluster_fill(ptr(ball_query_idxs), ptr(start_len), N, nC, s.value, ptr(cluster_idxs),
+                               ptr(cluster_offsets), ptr(ws), ws.numel(), _stream()), 'sgb_bfs_cluster_fill')
+    return cluster_idxs, cluster_offsets
+
+
+class BFSCluster(Function):
+    """functions.py:278-308. threshold semantics of bfs_cluster.cpp:70-82."""
+
+    @staticmethod
+    def forward(ctx, cluster_numpoint_mean, ball_query_idxs, start_len, threshold, class_id):
+        assert cluster_numpoint_mean.is_contiguous()
+        assert ball_query_idxs.is_contiguous()
+        assert start_len.is_contiguous()
+        mean = float(cluster_numpoint_mean[class_id])
+        # float32 arithmetic like the C++ (`thr = threshold * _class_numpoint_mean`, both float)
+        thr = float(threshold) if mean == -1 else float(
+            torch.tensor(threshold, dtype=torch.float32) * torch.tensor(mean, dtype=torch.float32))
+        on_cpu = not ball_query_idxs.is_cuda
+        idxs = _cuda(ball_query_idxs)
+        sl = _cuda(start_len)
+        if idxs.numel() == 0:
+            idxs = torch.zeros(1, dtype=torch.int32, device=sl.device)
+        cidx, coff = bfs_cluster_segments(idxs, sl, thr)
+        if on_cpu:
+            cidx, coff = cidx.cpu(), coff.cpu()
+        return cidx, coff
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None, None, None, None
+
+
+bfs_cluster = BFSCluster.apply
+
+
+# ----------------------------------------------------------------------------------------------
+# voxelisation
+# ----------------------------------------------------------------------------------------------
+class Voxelization_Idx(Function):
+    """functions.py:168-197 -> (output_coords, input_map, output_map)."""
+
+    @staticmethod
+    def forward(ctx, coords, batchsize, mode=4):
+        assert coords.is_contiguous() and coords.dtype == torch.int64
+        L = _lib.lib()
+        N, ncol = coords.size(0), coords.size(1)
+        M = ctypes.c_int(0)
+        mx = ctypes.c_int(0)
+        if coords.is_cuda:
+            dev = coords.device
+            input_map = torch.empty(N, dtype=torch.int32, device=dev)
+            ws = _ws(L.sgb_voxelize_idx_workspace_bytes(N), dev)
+            check(
+                L.sgb_voxelize_idx_count(ptr(coords), N, ncol, int(mode), ptr(input_map), ptr(ws), ws.numel(),
+                                         ctypes.byref(M), ctypes.byref(mx), _stream()), 'sgb_voxelize_idx_count')
+            output_coords = torch.empty((M.value, ncol), dtype=torch.int64, device=dev)
+            output_map = torch.empty((M.value, mx.value + 1), dtype=torch.int32, device=dev)
+            check(
+                L.sgb_voxelize_idx_fill(ptr(coords), N, ncol, int(mode), M.value, mx.value, ptr(output_coords),
+                                        ptr(output_map), ptr(ws), ws.numel(), _stream()), 'sgb_voxelize_idx_fill')
+            return output_coords, input_map, output_map
+        input_map = torch.zeros(N, dtype=torch.int32)
+        h = L.sgb_voxelize_idx_cpu_begin(ptr(coords), N, ncol, int(mode), ptr(input_map), ctypes.byref(M),
+                                         ctypes.byref(mx))
+        check(h, 'sgb_voxelize_idx_cpu_begin')
+        output_coords = torch.zeros((M.value, ncol), dtype=torch.int64)
+        output_map = torch.zeros((M.value, mx.value + 1), dtype=torch.int32)
+        check(L.sgb_voxelize_idx_cpu_finish(ctypes.c_void_p(h), ptr(coords), ptr(output_coords), ptr(output_map)),
+              'sgb_voxelize_idx_cpu_finish')
+        return output_coords, input_map, output_map
+
+    @staticmethod
+    def backward(ctx, a=None, b=None, c=None):
+        return None, None, None
+
+
+voxelization_idx = Voxelization_Idx.apply
+
+
+class Voxelization(Function):
+    """functions.py:200-234."""
+
+    @staticmethod
+    def forward(ctx, feats, map_rule, mode=4):
+        assert map_rule.is_contiguous()
+        assert feats.is_contiguous()
+        assert feats.is_cuda and map_rule.is_cuda and feats.dtype == torch.float32
+        N, C = feats.size()
+        M = map_rule.size(0)
+        maxActive = map_rule.size(1) - 1
+        output_feats = torch.empty((M, C), dtype=torch.float32, device=feats.device)
+        ctx.for_backwards = (map_rule, mode, maxActive, N)
+        check(
+            _lib.lib().sgb_voxelize_fp(ptr(feats), ptr(output_feats), ptr(map_rule), int(mode), M, maxActive, C,
+                                       _stream()), 'sgb_voxelize_fp')
+        return output_feats
+
+    @staticmethod
+    def backward(ctx, d_output_feats):
+        map_rule, mode, maxActive, N = ctx.for_backwards
+        M, C = d_output_feats.size()
+        d_feats = torch.zeros((N, C), dtype=torch.float32, device=d_output_feats.device)
+        d_out = d_output_feats.contiguous()
+        check(
+            _lib.lib().sgb_voxelize_bp(ptr(d_out), ptr(d_feats), ptr(map_rule), int(mode), M, maxActive, C, _stream()),
+            'sgb_voxelize_bp')
+        return d_feats, None, None
+
+
+voxelization = Voxelization.apply
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling / segment reductions
+# ----------------------------------------------------------------------------------------------
+class GlobalAvgPool(Function):
+    """functions.py:311-348."""
+
+    @staticmethod
+    def forward(ctx, feats, proposals_offset):
+        nProposal = proposals_offset.size(0) - 1
+        sumNPoint, C = feats.size()
+        assert feats.is_contiguous() and feats.is_cuda
+        assert proposals_offset.is_contiguous() and proposals_offset.is_cuda
+        output_feats = torch.empty((nProposal, C), dtype=torch.float32, device=feats.device)
+        check(
+            _lib.lib().sgb_global_avg_pool_fp(ptr(feats), ptr(proposals_offset), ptr(output_feats), nProposal, C,
+                                              _stream()), 'sgb_global_avg_pool_fp')
+        ctx.for_backwards = (proposals_offset, sumNPoint)
+        return output_feats
+
+    @staticmethod
+    def backward(ctx, d_output_feats):
+        nProposal, C = d_output_feats.size()
+        proposals_offset, sumNPoint = ctx.for_backwards
+        d_feats = torch.zeros((sumNPoint, C), dtype=torch.float32, device=d_output_feats.device)
+        d_out = d_output_feats.contiguous()
+        check(
+            _lib.lib().sgb_global_avg_pool_bp(ptr(d_feats), ptr(proposals_offset), ptr(d_out), nProposal, C, _stream()),
+            'sgb_global_avg_pool_bp')
+        return d_feats, None
+
+
+global_avg_pool = GlobalAvgPool.apply
+
+
+def _sec(name):
+
+    class _Sec(Function):
+        """functions.py:351-438 (SecMean / SecMin / SecMax)."""
+
+        @staticmethod
+        def forward(ctx, inp, offsets):
+            nProposal = offsets.size(0) - 1
+            C = inp.size(1)
+            assert inp.is_contiguous() and inp.is_cuda
+            assert offsets.is_contiguous() and offsets.is_cuda
+            out = torch.empty((nProposal, C), dtype=torch.float32, device=inp.device)
+            check(getattr(_lib.lib(), name)(ptr(inp), ptr(offsets), ptr(out), nProposal, C, _stream()), name)
+            return out
+
+        @staticmethod
+        def backward(ctx, a=None):
+            return None, None
+
+    _Sec.__name__ = name
+    return _Sec.apply
+
+
+sec_mean = _sec('sgb_sec_mean')
+sec_min = _sec('sgb_sec_min')
+sec_max = _sec('sgb_sec_max')
+
+
+# ----------------------------------------------------------------------------------------------
+# mask IoU / labels (training-side members of the binding surface)
+# ----------------------------------------------------------------------------------------------
+def _pidx_col(proposals_idx):
+    # the reference passes proposals_idx[:, 1].contiguous() (softgroup/model/softgroup.py:189-191)
+    assert proposals_idx.dim() == 1
+    return proposals_idx
+
+
+class GetMaskIoUOnCluster(Function):
+    """functions.py:47-83."""
+
+    @staticmethod
+    def forward(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum):
+        nInstance = instance_pointnum.size(0)
+        nProposal = proposals_offset.size(0) - 1
+        assert proposals_idx.is_contiguous() and proposals_idx.is_cuda
+        assert proposals_offset.is_contiguous() and proposals_offset.is_cuda
+        assert instance_labels.is_contiguous() and instance_labels.is_cuda
+        assert instance_pointnum.is_contiguous() and instance_pointnum.is_cuda
+        proposals_iou = torch.zeros((nProposal, nInstance), dtype=torch.float32, device=proposals_idx.device)
+        check(
+            _lib.lib().sgb_get_mask_iou(ptr(_pidx_col(proposals_idx)), ptr(proposals_offset), ptr(instance_labels),
+                                        ptr(instance_pointnum), None, ptr(proposals_iou), nInstance, nProposal,
+                                        _stream()), 'sgb_get_mask_iou')
+        return proposals_iou
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+get_mask_iou_on_cluster = GetMaskIoUOnCluster.apply
+
+
+class GetMaskIoUOnPred(Function):
+    """functions.py:86-125."""
+
+    @staticmethod
+    def forward(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum, mask_scores_sigmoid):
+        nInstance = instance_pointnum.size(0)
+        nProposal = proposals_offset.size(0) - 1
+        assert proposals_idx.is_contiguous() and proposals_idx.is_cuda
+        assert proposals_offset.is_contiguous() and proposals_offset.is_cuda
+        assert instance_labels.is_contiguous() and instance_labels.is_cuda
+        assert instance_pointnum.is_contiguous() and instance_pointnum.is_cuda
+        assert mask_scores_sigmoid.is_contiguous() and mask_scores_sigmoid.is_cuda
+        proposals_iou = torch.zeros((nProposal, nInstance), dtype=torch.float32, device=proposals_idx.device)
+        check(
+            _lib.lib().sgb_get_mask_iou(ptr(_pidx_col(proposals_idx)), ptr(proposals_offset), ptr(instance_labels),
+                                        ptr(instance_pointnum), ptr(mask_scores_sigmoid), ptr(proposals_iou), nInstance,
+                                        nProposal, _stream()), 'sgb_get_mask_iou')
+        return proposals_iou
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None, None
+
+
+get_mask_iou_on_pred = GetMaskIoUOnPred.apply
+
+
+class GetMaskLabel(Function):
+    """functions.py:128-165."""
+
+    @staticmethod
+    def forward(ctx, proposals_idx, proposals_offset, instance_labels, instance_cls, instance_pointnum, proposals_iou,
+                iou_thr):
+        nInstance = instance_pointnum.size(0)
+        nProposal = proposals_offset.size(0) - 1
+        assert proposals_iou.is_contiguous() and proposals_iou.is_cuda
+        assert proposals_idx.is_contiguous() and proposals_idx.is_cuda
+        assert proposals_offset.is_contiguous() and proposals_offset.is_cuda
+        assert instance_labels.is_contiguous() and instance_labels.is_cuda
+        assert instance_cls.is_contiguous() and instance_cls.is_cuda
+        mask_label = torch.full(proposals_idx.shape, -1.0, dtype=torch.float32, device=proposals_idx.device)
+        check(
+            _lib.lib().sgb_get_mask_label(ptr(_pidx_col(proposals_idx)), ptr(proposals_offset), ptr(instance_labels),
+                                          ptr(instance_cls), ptr(proposals_iou), nInstance, nProposal, float(iou_thr),
+                                          ptr(mask_label), _stream()), 'sgb_get_mask_label')
+        return mask_label
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None, None, None, None
+
+
+get_mask_label = GetMaskLabel.apply

@@ -1,0 +1,158 @@
+"""Synthetic scans shaped like the reference's datasets (no dataset files exist offline).
+
+Follows SURVEY.md section 8(d): float32 xyz in metres centred by the mean
+(dataset/scannetv2/prepare_data_inst.py:55), rgb in [-1,1] (:56), then the reference test
+transform: rotate 0.35*pi about z, * scale, - min, .long() (softgroup/data/custom.py:103-107,
+162-166, 180) and the collate layout of custom.py:191-256 (coords int64 [N,4] with the batch
+index in column 0, coords_float f32 [N,3], feats f32 [N,3], labels, spatial_shape).
+
+numpy only; no CUDA, no oracle.
+"""
+import math
+
+import numpy as np
+
+# name -> (n_points, room size m, n_objects, semantic classes, stuff classes, voxel scale)
+SHAPES = {
+    'c1_plumbing': dict(n=2000, room=(2.0, 2.0, 1.0), n_obj=4, sem=20, stuff=(0, 1), scale=50, walls=False),
+    'c2_scannet': dict(n=150000, room=(7.0, 5.0, 2.6), n_obj=40, sem=20, stuff=(0, 1), scale=50, walls=True),
+    'c3_s3dis': dict(n=800000, room=(15.0, 12.0, 3.0), n_obj=120, sem=13, stuff=(0, 1), scale=50, walls=True),
+    'c4_kitti': dict(n=120000, room=(60.0, 60.0, 3.0), n_obj=30, sem=19, stuff=tuple(range(0, 11)), scale=20,
+                     walls=False),
+    'c5_stpls3d': dict(n=1500000, room=(250.0, 250.0, 30.0), n_obj=400, sem=15, stuff=(0, ), scale=3, walls=False),
+}
+
+
+def _box_faces(lo, hi, with_bottom=False):
+    """Faces of an axis-aligned box as (origin, edge_u, edge_v) triples."""
+    lo = np.asarray(lo, np.float64)
+    hi = np.asarray(hi, np.float64)
+    d = hi - lo
+    faces = []
+    for ax in range(3):
+        u, v = [a for a in range(3) if a != ax]
+        for side in (0, 1):
+            if ax == 2 and side == 0 and not with_bottom:
+                continue
+            o = lo.copy()
+            if side:
+                o[ax] = hi[ax]
+            eu = np.zeros(3)
+            ev = np.zeros(3)
+            eu[u] = d[u]
+            ev[v] = d[v]
+            faces.append((o, eu, ev))
+    return faces
+
+
+def make_scan(shape='c2_scannet', seed=0, n_points=None, batch_id=0):
+    """One synthetic scan. Returns a dict of numpy arrays in the reference collate layout (one item)."""
+    cfg = dict(SHAPES[shape])
+    if n_points is not None:
+        cfg['n'] = int(n_points)
+    rng = np.random.RandomState(seed)
+    n = cfg['n']
+    rx, ry, rz = cfg['room']
+    thing_classes = [c for c in range(cfg['sem']) if c not in cfg['stuff']]
+
+    surfaces = []  # (origin, eu, ev, sem, inst)
+    surfaces.append((np.zeros(3), np.array([rx, 0, 0.]), np.array([0, ry, 0.]), cfg['stuff'][-1], -100))  # floor
+    if cfg['walls']:
+        w = cfg['stuff'][0]
+        surfaces.append((np.zeros(3), np.array([rx, 0, 0.]), np.array([0, 0, rz]), w, -100))
+        surfaces.append((np.array([0, ry, 0.]), np.array([rx, 0, 0.]), np.array([0, 0, rz]), w, -100))
+        surfaces.append((np.zeros(3), np.array([0, ry, 0.]), np.array([0, 0, rz]), w, -100))
+        surfaces.append((np.array([rx, 0, 0.]), np.array([0, ry, 0.]), np.array([0, 0, rz]), w, -100))
+    smax = min(1.8, 0.45 * min(rx, ry)) if rx < 100 else 12.0
+    smin = 0.3 if rx < 100 else 3.0
+    for k in range(cfg['n_obj']):
+        size = rng.uniform(smin, smax, 3)
+        size[2] = min(size[2], 0.9 * rz)
+        lo = np.array([rng.uniform(0, rx - size[0]), rng.uniform(0, ry - size[1]), 0.0])
+        cls = thing_classes[rng.randint(len(thing_classes))]
+        for (o, eu, ev) in _box_faces(lo, lo + size):
+            surfaces.append((o, eu, ev, cls, k))
+
+    areas = np.array([np.linalg.norm(np.cross(s[1], s[2])) for s in surfaces])
+    # keep floor/walls from swallowing the budget so that objects carry a realistic share of points
+    weight = areas.copy()
+    n_stuff = 5 if cfg['walls'] else 1
+    weight[:n_stuff] *= 0.35
+    counts = np.floor(weight / weight.sum() * n).astype(np.int64)
+    counts[0] += n - counts.sum()
+    xyz = np.empty((n, 3), np.float64)
+    sem = np.empty(n, np.int64)
+    inst = np.empty(n, np.int64)
+    pos = 0
+    for (o, eu, ev, c, k), m in zip(surfaces, counts):
+        uv = rng.rand(m, 2)
+        xyz[pos:pos + m] = o + uv[:, :1] * eu + uv[:, 1:] * ev
+        sem[pos:pos + m] = c
+        inst[pos:pos + m] = k
+        pos += m
+    xyz += rng.randn(n, 3) * 0.003
+    # interleave surfaces so that point order is not trivially sorted by object (ScanNet vertex order is
+    # spatially coherent but not grouped); a fixed-stride shuffle keeps some locality.
+    perm = rng.permutation(n)
+    xyz, sem, inst = xyz[perm], sem[perm], inst[perm]
+
+    palette = rng.uniform(-0.8, 0.8, (cfg['sem'], 3))
+    rgb = np.clip(palette[sem] + rng.randn(n, 3) * 0.1, -1, 1).astype(np.float32)
+    xyz = (xyz - xyz.mean(0)).astype(np.float32)
+
+    # reference test transform (custom.py:103-107 with aug off, :162-166)
+    theta = 0.35 * math.pi
+    m = np.eye(3)
+    m = np.matmul(m, [[math.cos(theta), math.sin(theta), 0], [-math.sin(theta), math.cos(theta), 0], [0, 0, 1]])
+    xyz_middle = np.matmul(xyz, m)  # float64, like the reference (numpy promotes)
+    xyz_scaled = xyz_middle * cfg['scale']
+    xyz_scaled -= xyz_scaled.min(0)
+    coord = xyz_scaled.astype(np.int64)  # torch.from_numpy(xyz).long() truncates toward zero (values >= 0)
+    coords_float = xyz_middle.astype(np.float32)
+
+    # instance info (custom.py:61-84): centroid offsets, per-instance point counts and classes
+    inst_ids = np.unique(inst[inst >= 0])
+    remap = -100 * np.ones(int(inst.max()) + 2, np.int64)
+    remap[inst_ids] = np.arange(len(inst_ids))
+    inst = np.where(inst >= 0, remap[np.clip(inst, 0, None)], -100)
+    pt_offset = np.zeros((n, 3), np.float32)
+    pointnum, cls = [], []
+    centroids = np.zeros((len(inst_ids), 3), np.float32)
+    for k in range(len(inst_ids)):
+        sel = inst == k
+        centroids[k] = coords_float[sel].mean(0)
+        pt_offset[sel] = centroids[k] - coords_float[sel]
+        pointnum.append(int(sel.sum()))
+        cls.append(int(sem[np.argmax(sel)]))
+
+    coords = np.concatenate([np.full((n, 1), batch_id, np.int64), coord], 1)
+    spatial_shape = np.clip(coord.max(0) + 1, 128, None)
+    return dict(
+        scan_ids=['synth_%s_seed%d' % (shape, seed)],
+        coords=coords,
+        batch_idxs=coords[:, 0].astype(np.int32),
+        coords_float=coords_float,
+        feats=rgb,
+        semantic_labels=sem,
+        instance_labels=inst,
+        instance_pointnum=np.asarray(pointnum, np.int32),
+        instance_cls=np.asarray(cls, np.int64),
+        pt_offset_labels=pt_offset,
+        spatial_shape=spatial_shape,
+        batch_size=1,
+        n_semantic=cfg['sem'],
+        stuff=cfg['stuff'],
+        scale=cfg['scale'],
+    )
+
+
+def grouping_inputs(scan, sigma=0.03, seed=0, logit=8.0):
+    """Stage inputs for forward_grouping (SURVEY.md 8(d) fallback): semantic scores = one-hot*logit + N(0,1),
+    pt_offsets = (centroid - xyz) + N(0, sigma)."""
+    rng = np.random.RandomState(seed + 1000)
+    n = scan['coords_float'].shape[0]
+    scores = rng.randn(n, scan['n_semantic']).astype(np.float32)
+    scores[np.arange(n), scan['semantic_labels']] += logit
+    off = scan['pt_offset_labels'] + (rng.randn(n, 3) * sigma).astype(np.float32)
+    off[scan['instance_labels'] < 0] = 0
+    return scores, off.astype(np.float32)
