@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the SoftGroup per-scan inference hot path on synthetic ScanNet-shape scans.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (the reference's CPU path on the host cores)
+
+A "step" is one pass of the hot path over one scan: GPU point->voxel hashing, voxel pooling, sparse U-Net,
+point heads, segmented ball query + BFS clustering, cluster re-voxelisation, tiny U-Net + heads, instance
+filtering. Workload = BASELINE.json configs[1] (ScanNet-shape, ~150k points, 18 instance classes), one scan
+per GPU per step (weak scaling, scans are independent; NCCL only reduces the timing).
+Prints ONE JSON line (see the contract in the task description / DESIGN.md section "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'scans/sec on 150k-pt ScanNet-shape synth'
+WORKLOAD = 'c2_scannet'
+N_POINTS = 150000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-points', type=int, default=20000)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = False
+        self.th = None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU path (oracle / compiled reference): cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------------
+def crop_scan(scan, n_keep):
+    """Spatially contiguous crop (same point density) holding ~n_keep points; labels re-indexed."""
+    from softgroup_b200 import synth  # noqa: F401
+    xyz = scan['coords_float']
+    n = xyz.shape[0]
+    if n_keep >= n:
+        return scan
+    # grow a box from the x-min side until it holds n_keep points
+    order = np.argsort(xyz[:, 0], kind='stable')
+    sel = np.sort(order[:n_keep])
+    out = {}
+    for k, v in scan.items():
+        if isinstance(v, np.ndarray) and v.shape[:1] == (n, ):
+            out[k] = v[sel]
+        else:
+            out[k] = v
+    c = out['coords'].copy()
+    c[:, 1:] -= c[:, 1:].min(0)
+    out['coords'] = c
+    out['spatial_shape'] = np.clip(c[:, 1:].max(0) + 1, 128, None)
+    return out
+
+
+def cpu_path_once(scan, sd, cfg, use_ref):
+    """One pass of the hot path on the host: reference CPU ops where the reference has them (voxelize_idx,
+    bfs_cluster -- compiled from its own sources in oracle/_ref), oracle restatements for the ops that are
+    CUDA-only in the reference (ball query, voxelize_fp, sec_*) and for the spconv-delegated sparse U-Net.
+    Returns (seconds, stage dict)."""
+    import torch
+    import oracle
+    from oracle import spconv_oracle as so
+    st = {}
+    t0 = time.perf_counter()
+    if use_ref is not None:
+        c = torch.from_numpy(scan['coords'])
+        oc, im, om = c.new(), torch.IntTensor(c.size(0)).zero_(), torch.IntTensor()
+        use_ref.voxelize_idx(c, oc, im, om, 1, 4)
+        vc, v2p, p2v = oc.numpy(), im.numpy(), om.numpy()
+    else:
+        vc, v2p, p2v = oracle.voxelization_idx(scan['coords'], 1, 4)
+    st['voxelize_idx'] = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    feats = np.concatenate([scan['feats'], scan['coords_float']], 1).astype(np.float32)
+    vfeats = oracle.voxelization(feats, p2v, 4)
+    out = so.backbone(vfeats, vc.astype(np.int32), scan['spatial_shape'], sd, cfg['channels'], cfg['num_blocks'])
+    pf = out[v2p]
+    st['backbone'] = time.perf_counter() - t1
+    t2 = time.perf_counter()
+
+    def mlp(x, p):
+        h = x @ sd[p + '.0.weight'].T + sd[p + '.0.bias']
+        h = so._bn_relu(h, sd, p + '.1')
+        return h @ sd[p + '.3.weight'].T + sd[p + '.3.bias']
+
+    sem = mlp(pf, 'semantic_linear')
+    off = mlp(pf, 'offset_linear')
+    e = np.exp(sem - sem.max(1, keepdims=True))
+    prob = e / e.sum(1, keepdims=True)
+    g = cfg['grouping_cfg']
+    mean = np.asarray(g['class_numpoint_mean'], np.float32)
+    nprop, nact = 0, 0
+    st['heads'] = time.perf_counter() - t2
+    tb = tq = 0.0
+    for c in range(cfg['semantic_classes']):
+        if c in g['ignore_classes']:
+            continue
+        sel = np.where(prob[:, c] > g['score_thr'])[0]
+        if sel.size < cfg['test_cfg']['min_npoint']:
+            continue
+        xyz = (scan['coords_float'][sel] + off[sel]).astype(np.float32)
+        t = time.perf_counter()
+        idx, sl = oracle.ballquery_batch_p(xyz, np.zeros(sel.size, np.int32), np.array([0, sel.size], np.int32),
+                                           g['radius'])
+        tq += time.perf_counter() - t
+        t = time.perf_counter()
+        if use_ref is not None:
+            ci, co = torch.IntTensor(), torch.IntTensor()
+            use_ref.bfs_cluster(torch.from_numpy(mean), torch.from_numpy(idx if idx.size else np.zeros(1, np.int32)),
+                                torch.from_numpy(sl), ci, co, int(sel.size), float(g['npoint_thr']), int(c))
+            nprop += co.numel() - 1
+        else:
+            ci, co = oracle.bfs_cluster(mean, idx, sl, g['npoint_thr'], c)
+            nprop += len(co) - 1
+        tb += time.perf_counter() - t
+        nact += idx.size
+    st['ballquery'] = tq
+    st['bfs_cluster'] = tb
+    total = time.perf_counter() - t0
+    st['nProposal'] = nprop
+    st['nActive'] = nact
+    return total, st
+
+
+def cpu_leg(args, sd, cfg, scan, steps, warmup):
+    import torch
+    from oracle.build_ref import load_ref
+    try:
+        ref = load_ref()
+    except Exception:
+        ref = None
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sub = crop_scan(scan, args.cpu_sample_points)
+    frac = sub['coords'].shape[0] / float(scan['coords'].shape[0])
+    times, stages = [], None
+    for it in range(warmup + steps):
+        t, st = cpu_path_once(sub, sd, cfg, ref)
+        if it >= warmup:
+            times.append(t)
+            stages = st
+    sec = float(np.mean(times))
+    kind = 'reference' if ref is not None else 'port'
+    sample = ('%d-point spatial crop (%.3f of a %d-point scan) through the CPU path: voxelize_idx + bfs_cluster = %s, '
+              'ball query / voxelize_fp / sparse U-Net (spconv) = oracle restatements (CUDA-only or third-party in '
+              'the reference); value = crop fraction / seconds; instance head not included' %
+              (sub['coords'].shape[0], frac, scan['coords'].shape[0],
+               'compiled reference (oracle/_ref)' if ref is not None else 'oracle port'))
+    return dict(value=frac / sec, unit='scans/sec', cores=cores, kind=kind, sample=sample,
+                ms_per_sample=sec * 1e3, stages_ms={k: (round(v * 1e3, 2) if isinstance(v, float) else v)
+                                                    for k, v in stages.items()}), sec
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+
+    import torch
+    from softgroup_b200 import synth
+    from softgroup_b200.configs import model_cfg
+
+    cfg = model_cfg('scannet')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        from softgroup_b200.model import SoftGroup
+        torch.manual_seed(0)
+        model = SoftGroup(**cfg).eval()
+        # identical synthetic checkpoint protocol, heads calibrated with the CPU fit below
+        scan = synth.make_scan(WORKLOAD, seed=args.seed, n_points=N_POINTS)
+        sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        sd = calibrate_sd_cpu(sd, cfg, crop_scan(scan, args.cpu_sample_points))
+        steps = max(1, min(args.steps, 3))
+        warm = min(args.warmup, 1)
+        cb, sec = cpu_leg(args, sd, cfg, scan, steps, warm)
+        line = dict(metric=METRIC, value=cb['value'], unit='scans/sec', n_gpus=args.gpus, steps=steps, warmup=warm,
+                    ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                    data='synthetic', impl='reference',
+                    config=dict(workload='ScanNet-shape synthetic scan (~150k pts, 18 classes), SoftGroup inference',
+                                note='reference arm steps are capped at 3 (each step is a bounded CPU sample)'),
+                    cpu_baseline=cb,
+                    e2e=dict(value=cb['value'], unit='scans/sec', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from softgroup_b200 import harness
+    from softgroup_b200.model import SoftGroup
+    from softgroup_b200.ops import _lib
+    from softgroup_b200 import profiler
+
+    torch.manual_seed(0)
+    model = SoftGroup(**cfg).cuda().eval()
+    scan = synth.make_scan(WORKLOAD, seed=args.seed + rank, n_points=N_POINTS)
+    hb = harness.to_host_batch(scan, pin=True)
+    calib = harness.calibrate_heads(model, hb)
+    dev = harness.device_batch(hb)
+    dev_in = {k: v for k, v in dev.items() if k not in ('voxel_coords', 'v2p_map', 'p2v_map')}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda')
+
+    def step_device():
+        # inputs resident in HBM; the step includes the GPU hash (point->voxel) and the whole forward
+        from softgroup_b200 import ops
+        vc, v2p, p2v = ops.voxelization_idx(dev_in['coords'], dev_in['batch_size'])
+        d = dict(dev_in)
+        d.pop('coords')
+        return model.forward_test(device_only=True, voxel_coords=vc, v2p_map=v2p, p2v_map=p2v, **d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, instrument=False):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            barrier()
+            evs = []
+            t_wall = time.perf_counter()
+            for _ in range(steps):
+                flush.zero_()  # L2 flush between iterations, outside the per-step events
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if instrument:
+                    profiler.enable()
+                e0.record()
+                out = fn()
+                e1.record()
+                if instrument:
+                    profiler.disable()
+                evs.append((e0, e1))
+            barrier()
+            wall = time.perf_counter() - t_wall
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms, wall, out
+
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        l0 = _lib.lib().sgb_launch_count()
+        dev_ms, dev_wall, out = timed(step_device, args.steps, max(args.warmup, 3))
+        launches = (_lib.lib().sgb_launch_count() - l0)
+        e2e_ms, e2e_wall, ret = timed(lambda: harness.run_scan(model, hb), args.steps, 2)
+        # instrumented pass (per-op CUDA events) -> dominant kernel and its roofline
+        profiler.reset()
+        timed(step_device, min(args.steps, 5), 1, instrument=True)
+    # launches counted over warmup+steps of the first leg -> per timed region
+    launches_per_step = launches // (args.steps + max(args.warmup, 3))
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    value = world * args.steps / (dev_ms_max / 1e3)
+    e2e_value = world * args.steps / (e2e_ms_max / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+        prof = profiler.summary()
+        dom = prof['dominant']
+        roofline = dict(bound='hbm', kernel=dom['name'], achieved=dom['gbs'], peak=hbm_peak, unit='GB/s',
+                        frac=dom['gbs'] / hbm_peak, traffic=None, peak_source=peak_src,
+                        launches_per_step=dom['launches_per_step'], avg_launch_us=dom['avg_us'],
+                        share_of_step=dom['share'], algorithmic_bytes_per_step=dom['bytes_per_step'],
+                        by_kernel=prof['by_kernel'])
+        d2h = 0
+        if isinstance(ret, dict):
+            d2h = int(sum(v.nbytes for v in ret.values() if isinstance(v, np.ndarray)))
+            d2h += int(sum(len(p['pred_mask']['counts']) for p in ret.get('pred_instances', [])))
+        line = dict(metric=METRIC, value=value, unit='scans/sec', n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=dev_ms_max / args.steps, higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                    config=dict(workload='ScanNet-shape synthetic scan (~150k pts, 18 classes), full SoftGroup '
+                                'inference, one scan per GPU per step', points=N_POINTS,
+                                model='SoftGroup 32ch x 7 blocks (softgroup_scannet.yaml), random init + closed-form '
+                                'calibrated point heads', l2='flushed: 512 MiB memset between timed steps',
+                                parallelism='dp%d (independent scans, no data-path collective)' % world,
+                                calibration=calib,
+                                voxels=int(out['semantic_preds'].numel()) if False else None),
+                    e2e=dict(value=e2e_value, unit='scans/sec', h2d_bytes_per_step=harness.h2d_bytes(hb),
+                             d2h_bytes_per_step=d2h, ms_per_step=e2e_ms_max / args.steps),
+                    gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
+                    clocks=sampler.summary(), roofline=roofline, stage_ms=prof.get('stage_ms'))
+        if not args.no_cpu_baseline and world == 1:
+            sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+            cb, _ = cpu_leg(args, sd, cfg, scan, 1, 0)
+            line['cpu_baseline'] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def calibrate_sd_cpu(sd, cfg, scan):
+    """CPU twin of harness.calibrate_heads for the reference arm (numpy, same ridge fit)."""
+    import oracle
+    from oracle import spconv_oracle as so
+    vc, v2p, p2v = oracle.voxelization_idx(scan['coords'], 1, 4)
+    feats = np.concatenate([scan['feats'], scan['coords_float']], 1).astype(np.float32)
+    out = so.backbone(oracle.voxelization(feats, p2v, 4), vc.astype(np.int32), scan['spatial_shape'], sd,
+                      cfg['channels'], cfg['num_blocks'])
+    pf = out[v2p].astype(np.float64)
+
+    def fit(p, target, ridge=1e-3):
+        h = pf @ sd[p + '.0.weight'].T.astype(np.float64) + sd[p + '.0.bias']
+        h = so._bn_relu(h.astype(np.float32), sd, p + '.1').astype(np.float64)
+        A = np.concatenate([h, np.ones((h.shape[0], 1))], 1)
+        G = A.T @ A + ridge * h.shape[0] * np.eye(A.shape[1])
+        sol = np.linalg.solve(G, A.T @ target)
+        sd[p + '.3.weight'] = sol[:-1].T.astype(np.float32)
+        sd[p + '.3.bias'] = sol[-1].astype(np.float32)
+
+    onehot = np.zeros((pf.shape[0], cfg['semantic_classes']))
+    onehot[np.arange(pf.shape[0]), scan['semantic_labels']] = 6.0
+    fit('semantic_linear', onehot)
+    off = scan['pt_offset_labels'].astype(np.float64).copy()
+    off[scan['instance_labels'] < 0] = 0
+    fit('offset_linear', off)
+    return sd
+
+
+if __name__ == '__main__':
+    sys.exit(main())

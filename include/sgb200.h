@@ -39,6 +39,8 @@ extern "C" {
 const char *sgb_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
 int sgb_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence). */
+long long sgb_launch_count(void);
 /* 1 if a CUDA device is usable, 0 otherwise (never initialises a context when none exists). */
 int sgb_device_available(void);
 

@@ -9,6 +9,7 @@
 namespace sgb {
 
 void set_error(const char *fmt, ...);
+void count_launch();  // bumps the process-wide kernel-launch counter (sgb_launch_count)
 
 #define SGB_CUDA_CHECK(expr)                                                              \
   do {                                                                                    \
@@ -19,7 +20,11 @@ void set_error(const char *fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define SGB_LAUNCH_CHECK() SGB_CUDA_CHECK(cudaGetLastError())
+#define SGB_LAUNCH_CHECK()               \
+  do {                                   \
+    sgb::count_launch();                 \
+    SGB_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
 
 #define SGB_REQUIRE(cond, code, msg)                                 \
   do {                                                               \

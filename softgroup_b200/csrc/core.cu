@@ -1,5 +1,6 @@
 // core.cu -- error reporting, device probe, device-wide exclusive scan.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,6 +8,9 @@
 namespace sgb {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -120,6 +124,8 @@ extern "C" {
 const char *sgb_last_error(void) { return sgb::g_err; }
 
 int sgb_abi_version(void) { return 1; }
+
+long long sgb_launch_count(void) { return sgb::g_launches.load(); }
 
 int sgb_device_available(void) {
   int n = 0;

@@ -1,0 +1,466 @@
+"""SoftGroup nn.Module -- inference forward of the reference's softgroup/model/softgroup.py on libsgb200.
+
+Same constructor arguments, same module tree / state_dict names (checkpoints load unchanged), same
+`forward(batch, return_loss=False)` entry and the same result dict as forward_test (softgroup.py:299-361).
+Only the inference path is built (training losses are out of scope).
+
+What is restructured underneath (same outputs):
+  * forward_grouping (softgroup.py:411-480): the 18-iteration per-class Python loop with >=6 host syncs per
+    class becomes ONE segmented ball query + ONE clustering call -- class c of batch item b is segment
+    (rank(c), b); segments are contiguous because entries are taken class-major in ascending point order,
+    which is exactly the order in which the reference concatenates its per-class results. Neighbour lists
+    never leave the GPU (the reference copies them to the CPU for BFS, :458).
+  * clusters_voxelization (:655-709): the hash runs on the GPU (the reference moves coords to the CPU, :701-703).
+  * get_instances (:537-604): no dense [nProposal, N] int masks; per (proposal, class) point counts come from a
+    segmented sum, kept masks are encoded to the reference's RLE wire format from sorted point ids.
+"""
+import functools
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import spconv
+from ..ops import (ballquery_batch_p, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
+                   voxelization_idx)
+from ..util import cuda_cast, force_fp32, rle_encode_ids
+from .blocks import MLP, ResidualBlock, UBlock
+
+
+class SoftGroup(nn.Module):
+
+    def __init__(self,
+                 in_channels=3,
+                 channels=32,
+                 num_blocks=7,
+                 semantic_only=False,
+                 semantic_classes=20,
+                 instance_classes=18,
+                 semantic_weight=None,
+                 sem2ins_classes=[],
+                 ignore_label=-100,
+                 with_coords=True,
+                 grouping_cfg=None,
+                 instance_voxel_cfg=None,
+                 train_cfg=None,
+                 test_cfg=None,
+                 fixed_modules=[]):
+        super().__init__()
+        self.in_channels = in_channels
+        self.channels = channels
+        self.num_blocks = num_blocks
+        self.semantic_only = semantic_only
+        self.semantic_classes = semantic_classes
+        self.instance_classes = instance_classes
+        self.semantic_weight = semantic_weight
+        self.sem2ins_classes = sem2ins_classes
+        self.ignore_label = ignore_label
+        self.with_coords = with_coords
+        self.grouping_cfg = grouping_cfg
+        self.instance_voxel_cfg = instance_voxel_cfg
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.fixed_modules = fixed_modules
+
+        block = ResidualBlock
+        norm_fn = functools.partial(nn.BatchNorm1d, eps=1e-4, momentum=0.1)
+
+        # backbone (softgroup.py:56-65)
+        if with_coords:
+            in_channels += 3
+            self.in_channels += 3
+        self.input_conv = spconv.SparseSequential(
+            spconv.SubMConv3d(in_channels, channels, kernel_size=3, padding=1, bias=False, indice_key='subm1'))
+        block_channels = [channels * (i + 1) for i in range(num_blocks)]
+        self.unet = UBlock(block_channels, norm_fn, 2, block, indice_key_id=1)
+        self.output_layer = spconv.SparseSequential(norm_fn(channels), nn.ReLU())
+
+        # point-wise prediction (:68-69)
+        self.semantic_linear = MLP(channels, semantic_classes, norm_fn=norm_fn, num_layers=2)
+        self.offset_linear = MLP(channels, 3, norm_fn=norm_fn, num_layers=2)
+
+        # top-down refinement path (:72-77)
+        if not semantic_only:
+            self.tiny_unet = UBlock([channels, 2 * channels], norm_fn, 2, block, indice_key_id=11)
+            self.tiny_unet_outputlayer = spconv.SparseSequential(norm_fn(channels), nn.ReLU())
+            self.cls_linear = nn.Linear(channels, instance_classes + 1)
+            self.mask_linear = MLP(channels, instance_classes + 1, norm_fn=None, num_layers=2)
+            self.iou_score_linear = nn.Linear(channels, instance_classes + 1)
+
+        self.init_weights()
+        for mod in fixed_modules:
+            mod = getattr(self, mod)
+            for param in mod.parameters():
+                param.requires_grad = False
+        self.stage_ms = None  # filled when profile_stages is set
+        self.profile_stages = False
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, MLP):
+                m.init_weights()
+        if not self.semantic_only:
+            for m in [self.cls_linear, self.iou_score_linear]:
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, batch, return_loss=False):
+        if return_loss:
+            raise NotImplementedError('softgroup_b200 builds the inference forward only (training is out of scope)')
+        return self.forward_test(**batch)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _cfg(self, cfg, name, default=None):
+        if isinstance(cfg, dict):
+            return cfg.get(name, default)
+        return getattr(cfg, name, default)
+
+    def _mark(self, name):
+        if self.profile_stages:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._events.append((name, ev))
+
+    @cuda_cast
+    def forward_test(self, batch_idxs, voxel_coords, p2v_map, v2p_map, coords_float, feats, semantic_labels=None,
+                     instance_labels=None, pt_offset_labels=None, spatial_shape=None, batch_size=1, scan_ids=None,
+                     **kwargs):
+        self._events = []
+        self._mark('start')
+        device_only = kwargs.get('device_only', False)  # bench: keep results on the GPU (no numpy / RLE)
+        tc = self.test_cfg
+        eval_tasks = self._cfg(tc, 'eval_tasks', ['semantic', 'instance'])
+        x4_split = self._cfg(tc, 'x4_split', False)
+        color_feats = feats
+        if self.with_coords:
+            feats = torch.cat((feats, coords_float), 1)
+        voxel_feats = voxelization(feats.contiguous(), p2v_map.contiguous())
+        input = spconv.SparseConvTensor(voxel_feats, voxel_coords.int(), spatial_shape, batch_size)
+        self._mark('voxelize')
+        lvl_fusion = self._cfg(tc, 'lvl_fusion', False)
+        assert not lvl_fusion, 'lvl_fusion (SoftGroup++) is not built yet'
+        semantic_scores, pt_offsets, output_feats = self.forward_backbone(input, v2p_map, x4_split=x4_split)
+        self._mark('backbone')
+        if x4_split:
+            coords_float = self.merge_4_parts(coords_float)
+            semantic_labels = self.merge_4_parts(semantic_labels)
+            instance_labels = self.merge_4_parts(instance_labels)
+            pt_offset_labels = self.merge_4_parts(pt_offset_labels)
+        semantic_preds = semantic_scores.max(1)[1]
+        ret = dict(scan_id=scan_ids[0] if scan_ids else None)
+        if not device_only:
+            if 'semantic' in eval_tasks or 'panoptic' in eval_tasks:
+                ret.update(dict(semantic_labels=semantic_labels.cpu().numpy(),
+                                instance_labels=instance_labels.cpu().numpy()))
+            if 'semantic' in eval_tasks:
+                ret.update(dict(coords_float=coords_float.cpu().numpy(), color_feats=color_feats.cpu().numpy(),
+                                semantic_preds=semantic_preds.cpu().numpy(), offset_preds=pt_offsets.cpu().numpy(),
+                                offset_labels=pt_offset_labels.cpu().numpy()))
+        if not self.semantic_only and ('instance' in eval_tasks or 'panoptic' in eval_tasks):
+            proposals_idx, proposals_offset = self.forward_grouping(semantic_scores, pt_offsets, batch_idxs,
+                                                                    coords_float, self.grouping_cfg)
+            self._mark('grouping')
+            inst_feats, inst_map = self.clusters_voxelization(proposals_idx, proposals_offset, output_feats,
+                                                              coords_float, **self._voxel_cfg())
+            self._mark('clusters_voxelization')
+            _, cls_scores, iou_scores, mask_scores = self.forward_instance(inst_feats, inst_map)
+            self._mark('instance_head')
+            inst = self.get_instances(scan_ids[0] if scan_ids else None, proposals_idx, semantic_scores, cls_scores,
+                                      iou_scores, mask_scores, device_only=device_only)
+            self._mark('get_instances')
+            if device_only:
+                ret.update(device_instances=inst, proposals_idx=proposals_idx, proposals_offset=proposals_offset)
+            else:
+                if 'instance' in eval_tasks:
+                    ret.update(dict(pred_instances=inst,
+                                    gt_instances=self.get_gt_instances(semantic_labels, instance_labels)))
+                if 'panoptic' in eval_tasks:
+                    ret.update(panoptic_preds=self.panoptic_fusion(semantic_preds.cpu().numpy(), inst))
+        if device_only:
+            ret.update(semantic_preds=semantic_preds, pt_offsets=pt_offsets)
+        if self.profile_stages:
+            torch.cuda.synchronize()
+            self.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._events[:-1], self._events[1:])}
+        return ret
+
+    def _voxel_cfg(self):
+        c = self.instance_voxel_cfg
+        return dict(c) if isinstance(c, dict) else {k: getattr(c, k) for k in ('scale', 'spatial_shape') if hasattr(c, k)}
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward_backbone(self, input, input_map, x4_split=False, lvl_fusion=False):
+        """softgroup.py:363-378."""
+        if x4_split:
+            output_feats = self.forward_4_parts(input, input_map)
+            output_feats = self.merge_4_parts(output_feats)
+        else:
+            output = self.input_conv(input)
+            output = self.unet(output)
+            output = self.output_layer(output)
+            from ..ops import _lib
+            from ..ops._lib import check, ptr
+            import ctypes
+            vf = output.features
+            N = input_map.size(0)
+            output_feats = torch.empty((N, vf.size(1)), dtype=vf.dtype, device=vf.device)
+            # output_feats[input_map.long()] (:374) -- the "devoxelize" gather
+            from .. import profiler
+            with profiler.record('gather_rows(devoxelize)', 4 * N + 4 * vf.size(1) * (vf.size(0) + N)):
+                check(_lib.lib().sgb_gather_rows(ptr(vf), ptr(input_map.contiguous()), ptr(output_feats), N,
+                                                 vf.size(1), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                      'sgb_gather_rows')
+        semantic_scores = self.semantic_linear(output_feats)
+        pt_offsets = self.offset_linear(output_feats)
+        return semantic_scores, pt_offsets, output_feats
+
+    def forward_4_parts(self, x, input_map):
+        """softgroup.py:380-395 (S3DIS): four interleaved quarter clouds through the backbone one after another."""
+        outs = []
+        for i in range(4):
+            inds = x.indices[:, 0] == i
+            feats = x.features[inds]
+            coords = x.indices[inds].clone()
+            coords[:, 0] = 0
+            x_new = spconv.SparseConvTensor(indices=coords, features=feats, spatial_shape=x.spatial_shape,
+                                            batch_size=1)
+            out = self.input_conv(x_new)
+            out = self.unet(out)
+            out = self.output_layer(out)
+            outs.append(out.features)
+        outs = torch.cat(outs, dim=0)
+        return outs[input_map.long()]
+
+    def merge_4_parts(self, x):
+        """softgroup.py:397-409."""
+        inds = torch.arange(x.size(0), device=x.device)
+        ps = [inds[0::4], inds[1::4], inds[2::4], inds[3::4]]
+        x_split = torch.split(x, [p.size(0) for p in ps])
+        x_new = torch.zeros_like(x)
+        for i, p in enumerate(ps):
+            x_new[p] = x_split[i]
+        return x_new
+
+    # ------------------------------------------------------------------------------------------------------
+    @force_fp32(apply_to=('semantic_scores, pt_offsets'))
+    def forward_grouping(self, semantic_scores, pt_offsets, batch_idxs, coords_float, grouping_cfg=None,
+                         lvl_fusion=False):
+        """softgroup.py:411-480, all classes in one segmented launch. Returns CUDA int32 tensors
+        proposals_idx [sumNPoint,2] (proposal id, point idx), proposals_offset [nProposal+1]."""
+        g = self.grouping_cfg
+        dev = semantic_scores.device
+        batch_size = int(batch_idxs.max().item()) + 1
+        scores = semantic_scores.softmax(dim=-1)
+        radius = float(self._cfg(g, 'radius'))
+        mean_active = int(self._cfg(g, 'mean_active'))
+        npoint_thr = float(self._cfg(g, 'npoint_thr'))
+        score_thr = float(self._cfg(g, 'score_thr'))
+        assert not self._cfg(g, 'with_pyramid', False) and not self._cfg(g, 'with_octree', False), \
+            'SoftGroup++ grouping (pyramid/octree) is not built yet'
+        cnm = self._cfg(g, 'class_numpoint_mean')
+        assert len(cnm) == self.semantic_classes
+        ignore = set(self._cfg(g, 'ignore_classes', []))
+        classes = [c for c in range(self.semantic_classes) if c not in ignore]
+        min_npoint = int(self._cfg(self.test_cfg, 'min_npoint', 0))
+        empty = (torch.zeros((0, 2), dtype=torch.int32, device=dev), torch.zeros((0, ), dtype=torch.int32, device=dev))
+        if not classes:
+            return empty
+        cls_t = torch.tensor(classes, device=dev)
+        mask = scores[:, cls_t] > score_thr  # [N, nc]
+        counts = mask.sum(0)
+        keep = counts >= min_npoint  # `object_idxs.size(0) < min_npoint -> continue` (:437-439)
+        mask = mask & keep[None, :]
+        ent = mask.t().nonzero()  # class-major, ascending point index: (class rank, point)
+        n = ent.size(0)
+        if n == 0:
+            return empty
+        crank = ent[:, 0]
+        pts = ent[:, 1]
+        seg = (crank * batch_size + batch_idxs[pts].long()).int().contiguous()
+        nseg = len(classes) * batch_size
+        seg_counts = torch.bincount(seg.long(), minlength=nseg)
+        seg_offsets = torch.zeros(nseg + 1, dtype=torch.int32, device=dev)
+        seg_offsets[1:] = seg_counts.cumsum(0).int()
+        shifted = (coords_float[pts] + pt_offsets[pts]).contiguous()
+        neighbor_inds, start_len = ballquery_batch_p(shifted, seg, seg_offsets, radius, mean_active)
+        # per-segment thresholds: threshold*mean or absolute when mean == -1 (bfs_cluster.cpp:70-77), float32 math
+        thr_c = torch.tensor([npoint_thr if cnm[c] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[c]))
+                              for c in classes], dtype=torch.float32, device=dev)
+        seg_thr = thr_c.repeat_interleave(batch_size).contiguous()
+        capped = False  # lists that hit the 1000 cap make the graph asymmetric -> exact directed labelling
+        cidx, coff = bfs_cluster_segments(neighbor_inds, start_len, 0.0, node_seg=seg, seg_thr=seg_thr,
+                                          symmetric=not capped)
+        if cidx.size(0) == 0:
+            return empty
+        # proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1]] (:464)
+        cidx[:, 1] = pts[cidx[:, 1].long()].int()
+        return cidx, coff
+
+    # ------------------------------------------------------------------------------------------------------
+    @force_fp32(apply_to='feats')
+    def clusters_voxelization(self, clusters_idx, clusters_offset, feats, coords, scale, spatial_shape,
+                              rand_quantize=False):
+        """softgroup.py:655-709 with the hash on the GPU."""
+        dev = feats.device
+        if clusters_idx.size(0) == 0:
+            coords = torch.tensor([[0, 0, 0, 0], [0, spatial_shape - 1, spatial_shape - 1, spatial_shape - 1]],
+                                  dtype=torch.int, device=dev)
+            feats = feats[0:2]
+            voxelization_feats = spconv.SparseConvTensor(feats, coords, [spatial_shape] * 3, 1)
+            inp_map = feats.new_zeros((1, ), dtype=torch.long)
+            return voxelization_feats, inp_map
+        clusters_idx = clusters_idx.to(dev)
+        clusters_offset = clusters_offset.to(dev).contiguous()
+        batch_idx = clusters_idx[:, 0].long()
+        c_idxs = clusters_idx[:, 1].long()
+        feats = feats[c_idxs]
+        coords = coords[c_idxs].contiguous()
+        coords_min = sec_min(coords, clusters_offset)
+        coords_max = sec_max(coords, clusters_offset)
+        # 0.01 to ensure voxel_coords < spatial_shape (:682-683)
+        clusters_scale = 1 / ((coords_max - coords_min) / spatial_shape).max(1)[0] - 0.01
+        clusters_scale = torch.clamp(clusters_scale, min=None, max=scale)
+        coords_min = coords_min * clusters_scale[:, None]
+        coords_max = coords_max * clusters_scale[:, None]
+        clusters_scale = clusters_scale[batch_idx]
+        coords = coords * clusters_scale[:, None]
+        assert not rand_quantize, 'rand_quantize is a training-time augmentation'
+        coords_min = coords_min[batch_idx]
+        coords -= coords_min
+        coords = coords.long()
+        coords = torch.cat([batch_idx.view(-1, 1), coords], 1).contiguous()
+        n_clusters = clusters_offset.numel() - 1
+        out_coords, inp_map, out_map = voxelization_idx(coords, n_clusters)
+        out_feats = voxelization(feats.contiguous(), out_map)
+        voxelization_feats = spconv.SparseConvTensor(out_feats, out_coords.int(), [spatial_shape] * 3, n_clusters)
+        return voxelization_feats, inp_map
+
+    def forward_instance(self, inst_feats, inst_map):
+        """softgroup.py:509-522."""
+        feats = self.tiny_unet(inst_feats)
+        feats = self.tiny_unet_outputlayer(feats)
+        mask_scores = self.mask_linear(feats.features)
+        mask_scores = mask_scores[inst_map.long()]
+        instance_batch_idxs = feats.indices[:, 0][inst_map.long()]
+        feats = self.global_pool(feats)
+        cls_scores = self.cls_linear(feats)
+        iou_scores = self.iou_score_linear(feats)
+        return instance_batch_idxs, cls_scores, iou_scores, mask_scores
+
+    @force_fp32(apply_to=('x'))
+    def global_pool(self, x, expand=False):
+        """softgroup.py:718-731."""
+        indices = x.indices[:, 0]
+        batch_counts = torch.bincount(indices.long(), minlength=int(x.batch_size))
+        batch_offset = torch.zeros(batch_counts.numel() + 1, dtype=torch.int32, device=indices.device)
+        batch_offset[1:] = torch.cumsum(batch_counts, dim=0).int()
+        x_pool = global_avg_pool(x.features.contiguous(), batch_offset)
+        if not expand:
+            return x_pool
+        x_pool_expand = x_pool[indices.long()]
+        x.features = torch.cat((x.features, x_pool_expand), dim=1)
+        return x
+
+    # ------------------------------------------------------------------------------------------------------
+    @force_fp32(apply_to=('semantic_scores', 'cls_scores', 'iou_scores', 'mask_scores'))
+    def get_instances(self, scan_id, proposals_idx, semantic_scores, cls_scores, iou_scores, mask_scores,
+                      v2p_map=None, lvl_fusion=False, device_only=False):
+        """softgroup.py:537-604 without dense masks.
+
+        For every instance class i and proposal p (class-major, proposal order -- the order in which the reference
+        concatenates its lists): kept iff cls_score[p,i] > cls_score_thr and
+        #{points of p with mask_score[:, i] > mask_score_thr} >= min_npoint."""
+        if proposals_idx.size(0) == 0:
+            return []
+        tc = self.test_cfg
+        mask_thr = float(self._cfg(tc, 'mask_score_thr'))
+        cls_thr = float(self._cfg(tc, 'cls_score_thr'))
+        min_npoint = int(self._cfg(tc, 'min_npoint'))
+        num_instances = cls_scores.size(0)
+        num_points = semantic_scores.size(0)
+        nI = self.instance_classes
+        cls_sm = cls_scores.softmax(1)
+        pid = proposals_idx[:, 0].long()
+        on = mask_scores[:, :nI] > mask_thr  # [sumNPoint, nI]
+        npoint = torch.zeros((num_instances, nI), dtype=torch.int32, device=on.device)
+        npoint.index_add_(0, pid, on.int())
+        score = cls_sm[:, :nI] * iou_scores[:, :nI].clamp(0, 1)
+        keep = (cls_sm[:, :nI] > cls_thr) & (npoint >= min_npoint)  # [nProp, nI]
+        for i in self.sem2ins_classes:
+            keep[:, i] = False
+        if device_only:
+            return dict(keep=keep, score=score, npoint=npoint, on=on)
+        instances = []
+        semantic_pred = None
+        keep_t = keep.t().contiguous()  # class-major
+        kc, kp = keep_t.nonzero(as_tuple=True)
+        conf = score.t()[kc, kp]
+        # (class, proposal) -> rank among kept instances; expand to the points of kept masks
+        rank = torch.full((nI, num_instances), -1, dtype=torch.long, device=on.device)
+        rank[kc, kp] = torch.arange(kc.numel(), device=on.device)
+        pr = rank[:, pid].t()  # [sumNPoint, nI] rank of (class i, proposal of this point)
+        sel = on & (pr >= 0)
+        rows, cols = sel.nonzero(as_tuple=True)
+        inst_rank = pr[rows, cols]
+        pt = proposals_idx[:, 1].long()[rows]
+        order = torch.argsort(inst_rank * num_points + pt)
+        inst_rank, pt = inst_rank[order], pt[order]
+        counts = torch.bincount(inst_rank, minlength=kc.numel())
+        pt_np = pt.cpu().numpy()
+        counts_np = counts.cpu().numpy()
+        kc_np, conf_np = kc.cpu().numpy(), conf.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(counts_np)])
+        k = 0
+        for i in range(nI):
+            if i in self.sem2ins_classes:
+                if semantic_pred is None:
+                    semantic_pred = semantic_scores.max(1)[1]
+                ids = (semantic_pred == i).nonzero().view(-1).cpu().numpy()
+                instances.append(dict(scan_id=scan_id, label_id=i + 1, conf=np.float32(1.),
+                                      pred_mask=rle_encode_ids(ids, num_points)))
+                continue
+            while k < kc_np.size and kc_np[k] == i:
+                instances.append(dict(scan_id=scan_id, label_id=i + 1, conf=conf_np[k],
+                                      pred_mask=rle_encode_ids(pt_np[offs[k]:offs[k + 1]], num_points)))
+                k += 1
+        return instances
+
+    def panoptic_fusion(self, semantic_preds, instance_preds):
+        """softgroup.py:606-639 (CPU numpy paste loop; SURVEY.md N3 lists it as a next row)."""
+        from ..util import rle_decode
+        cls_offset = self.semantic_classes - self.instance_classes - 1
+        panoptic_cls = semantic_preds.copy().astype(np.uint32)
+        panoptic_ids = np.zeros_like(semantic_preds).astype(np.uint32)
+        scores = [x['conf'] for x in instance_preds]
+        score_inds = np.argsort(scores)[::-1]
+        prev_paste = np.zeros_like(semantic_preds, dtype=bool)
+        panoptic_id = 1
+        for i in score_inds:
+            instance = instance_preds[i]
+            cls = instance['label_id']
+            mask = rle_decode(instance['pred_mask']).astype(bool)
+            intersect = (mask * prev_paste).sum()
+            if intersect / (mask.sum() + 1e-5) > self._cfg(self.test_cfg, 'panoptic_skip_iou'):
+                continue
+            paste = mask * (~prev_paste)
+            panoptic_cls[paste] = cls + cls_offset
+            panoptic_ids[paste] = panoptic_id
+            prev_paste[paste] = 1
+            panoptic_id += 1
+        ignore_inds = (panoptic_cls >= 11) & (panoptic_ids == 0)
+        panoptic_preds = (panoptic_cls & 0xFFFF) | (panoptic_ids << 16)
+        panoptic_preds[ignore_inds] = self.semantic_classes
+        return panoptic_preds.astype(np.uint32)
+
+    def get_gt_instances(self, semantic_labels, instance_labels):
+        """softgroup.py:641-653."""
+        label_shift = self.semantic_classes - self.instance_classes
+        semantic_labels = semantic_labels - label_shift + 1
+        semantic_labels[semantic_labels < 0] = 0
+        instance_labels = instance_labels + 1
+        ignore_inds = instance_labels < 0
+        gt_ins = semantic_labels * 1000 + instance_labels
+        gt_ins[ignore_inds] = 0
+        return gt_ins.cpu().numpy()

@@ -19,6 +19,7 @@ SIGNATURES = {
     'sgb_last_error': (ctypes.c_char_p, []),
     'sgb_abi_version': (c_int, []),
     'sgb_device_available': (c_int, []),
+    'sgb_launch_count': (c_longlong, []),
     'sgb_voxelize_idx_workspace_bytes': (c_size_t, [c_int]),
     'sgb_voxelize_idx_count': (c_int, [_P, c_int, c_int, c_int, _P, _P, c_size_t, _INTP, _INTP, _P]),
     'sgb_voxelize_idx_fill': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),

@@ -19,6 +19,7 @@ import ctypes
 import torch
 from torch.autograd import Function
 
+from .. import profiler
 from . import _lib
 from ._lib import check, ptr
 
@@ -69,10 +70,13 @@ class BallQueryBatchP(Function):
         meanActive = int(meanActive)
         while True:
             idx = torch.empty(max(n * meanActive, 1), dtype=torch.int32, device=dev)
-            nActive = check(
-                L.sgb_ballquery_batch_p(n, meanActive, float(radius), ptr(coords), ptr(batch_idxs), ptr(batch_offsets),
-                                        B, ptr(idx), ptr(start_len), ptr(ws), ws.numel(), _stream()),
-                'sgb_ballquery_batch_p')
+            rec = profiler.record('ballquery_batch_p')
+            with rec:
+                nActive = check(
+                    L.sgb_ballquery_batch_p(n, meanActive, float(radius), ptr(coords), ptr(batch_idxs),
+                                            ptr(batch_offsets), B, ptr(idx), ptr(start_len), ptr(ws), ws.numel(),
+                                            _stream()), 'sgb_ballquery_batch_p')
+                rec.nbytes = 24 * n + 4 * (B + 1) + 4 * min(nActive, n * meanActive)
             if nActive <= n * meanActive:
                 break
             meanActive = int(nActive // n + 1)
@@ -98,15 +102,18 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     N = start_len.size(0)
     ws = _ws(L.sgb_bfs_cluster_workspace_bytes(N), dev)
     s = ctypes.c_int(0)
-    nC = check(
-        L.sgb_bfs_cluster_count(ptr(ball_query_idxs), ptr(start_len), N, float(thr), ptr(node_seg), ptr(seg_thr),
-                                int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), _stream()),
-        'sgb_bfs_cluster_count')
+    nact = ball_query_idxs.numel()
+    with profiler.record('bfs_cluster(label)', 8 * N + 4 * nact):
+        nC = check(
+            L.sgb_bfs_cluster_count(ptr(ball_query_idxs), ptr(start_len), N, float(thr), ptr(node_seg), ptr(seg_thr),
+                                    int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), _stream()),
+            'sgb_bfs_cluster_count')
     cluster_idxs = torch.empty((s.value, 2), dtype=torch.int32, device=dev)
     cluster_offsets = torch.empty(nC + 1, dtype=torch.int32, device=dev)
-    check(
-        L.sgb_bfs_cluster_fill(ptr(ball_query_idxs), ptr(start_len), N, nC, s.value, ptr(cluster_idxs),
-                               ptr(cluster_offsets), ptr(ws), ws.numel(), _stream()), 'sgb_bfs_cluster_fill')
+    with profiler.record('bfs_cluster(emit)', 8 * N + 4 * nact + 8 * s.value + 4 * (nC + 1)):
+        check(
+            L.sgb_bfs_cluster_fill(ptr(ball_query_idxs), ptr(start_len), N, nC, s.value, ptr(cluster_idxs),
+                                   ptr(cluster_offsets), ptr(ws), ws.numel(), _stream()), 'sgb_bfs_cluster_fill')
     return cluster_idxs, cluster_offsets
 
 
@@ -157,14 +164,17 @@ class Voxelization_Idx(Function):
             dev = coords.device
             input_map = torch.empty(N, dtype=torch.int32, device=dev)
             ws = _ws(L.sgb_voxelize_idx_workspace_bytes(N), dev)
-            check(
-                L.sgb_voxelize_idx_count(ptr(coords), N, ncol, int(mode), ptr(input_map), ptr(ws), ws.numel(),
-                                         ctypes.byref(M), ctypes.byref(mx), _stream()), 'sgb_voxelize_idx_count')
-            output_coords = torch.empty((M.value, ncol), dtype=torch.int64, device=dev)
-            output_map = torch.empty((M.value, mx.value + 1), dtype=torch.int32, device=dev)
-            check(
-                L.sgb_voxelize_idx_fill(ptr(coords), N, ncol, int(mode), M.value, mx.value, ptr(output_coords),
-                                        ptr(output_map), ptr(ws), ws.numel(), _stream()), 'sgb_voxelize_idx_fill')
+            rec = profiler.record('voxelize_idx')
+            with rec:
+                check(
+                    L.sgb_voxelize_idx_count(ptr(coords), N, ncol, int(mode), ptr(input_map), ptr(ws), ws.numel(),
+                                             ctypes.byref(M), ctypes.byref(mx), _stream()), 'sgb_voxelize_idx_count')
+                output_coords = torch.empty((M.value, ncol), dtype=torch.int64, device=dev)
+                output_map = torch.empty((M.value, mx.value + 1), dtype=torch.int32, device=dev)
+                check(
+                    L.sgb_voxelize_idx_fill(ptr(coords), N, ncol, int(mode), M.value, mx.value, ptr(output_coords),
+                                            ptr(output_map), ptr(ws), ws.numel(), _stream()), 'sgb_voxelize_idx_fill')
+                rec.nbytes = 8 * ncol * N + 4 * N + 8 * ncol * M.value + 4 * M.value * (mx.value + 1)
             return output_coords, input_map, output_map
         input_map = torch.zeros(N, dtype=torch.int32)
         h = L.sgb_voxelize_idx_cpu_begin(ptr(coords), N, ncol, int(mode), ptr(input_map), ctypes.byref(M),
@@ -197,9 +207,10 @@ class Voxelization(Function):
         maxActive = map_rule.size(1) - 1
         output_feats = torch.empty((M, C), dtype=torch.float32, device=feats.device)
         ctx.for_backwards = (map_rule, mode, maxActive, N)
-        check(
-            _lib.lib().sgb_voxelize_fp(ptr(feats), ptr(output_feats), ptr(map_rule), int(mode), M, maxActive, C,
-                                       _stream()), 'sgb_voxelize_fp')
+        with profiler.record('voxelize_fp', 4 * M * (maxActive + 1) + 4 * C * (N + M)):
+            check(
+                _lib.lib().sgb_voxelize_fp(ptr(feats), ptr(output_feats), ptr(map_rule), int(mode), M, maxActive, C,
+                                           _stream()), 'sgb_voxelize_fp')
         return output_feats
 
     @staticmethod
@@ -230,9 +241,10 @@ class GlobalAvgPool(Function):
         assert feats.is_contiguous() and feats.is_cuda
         assert proposals_offset.is_contiguous() and proposals_offset.is_cuda
         output_feats = torch.empty((nProposal, C), dtype=torch.float32, device=feats.device)
-        check(
-            _lib.lib().sgb_global_avg_pool_fp(ptr(feats), ptr(proposals_offset), ptr(output_feats), nProposal, C,
-                                              _stream()), 'sgb_global_avg_pool_fp')
+        with profiler.record('global_avg_pool', 4 * C * sumNPoint + 4 * (nProposal + 1) + 4 * C * nProposal):
+            check(
+                _lib.lib().sgb_global_avg_pool_fp(ptr(feats), ptr(proposals_offset), ptr(output_feats), nProposal, C,
+                                                  _stream()), 'sgb_global_avg_pool_fp')
         ctx.for_backwards = (proposals_offset, sumNPoint)
         return output_feats
 
@@ -263,7 +275,8 @@ def _sec(name):
             assert inp.is_contiguous() and inp.is_cuda
             assert offsets.is_contiguous() and offsets.is_cuda
             out = torch.empty((nProposal, C), dtype=torch.float32, device=inp.device)
-            check(getattr(_lib.lib(), name)(ptr(inp), ptr(offsets), ptr(out), nProposal, C, _stream()), name)
+            with profiler.record(name[4:], 4 * C * inp.size(0) + 4 * (nProposal + 1) + 4 * C * nProposal):
+                check(getattr(_lib.lib(), name)(ptr(inp), ptr(offsets), ptr(out), nProposal, C, _stream()), name)
             return out
 
         @staticmethod

@@ -1,0 +1,354 @@
+"""spconv-shaped surface used by the reference model, on libsgb200 kernels (no spconv dependency).
+
+Covers exactly what softgroup/model/blocks.py, softgroup/model/softgroup.py and softgroup/util/fp16.py touch
+(SURVEY.md 8b): SparseConvTensor(.features .indices .spatial_shape .batch_size .indice_dict .grid
+.replace_feature), SparseSequential, SparseModule, SubMConv3d / SparseConv3d / SparseInverseConv3d with
+`.weight [out,k,k,k,in]`, `.in_channels`, `.out_channels`, `.bias`, `indice_key` rulebook sharing.
+
+Inference-only: BatchNorm1d must be in eval mode; it is folded to (scale, shift) and, together with a following
+ReLU, fused into the input transform of the next sparse convolution (the pre-activation pattern of
+blocks.py:55-70). SparseSequential does that peephole fusion itself, so the reference's module tree and
+state_dict names stay untouched.
+"""
+import ctypes
+import weakref
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from .. import profiler
+from ..ops import _lib
+from ..ops._lib import check, ptr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SparseConvTensor(object):
+
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, indice_dict=None):
+        self.features = features
+        self.indices = indices
+        self.spatial_shape = [int(s) for s in spatial_shape]
+        self.batch_size = batch_size
+        self.indice_dict = indice_dict if indice_dict is not None else {}
+        self.grid = grid
+
+    def replace_feature(self, feature):
+        out = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid,
+                               self.indice_dict)
+        return out
+
+    @property
+    def spatial_size(self):
+        n = 1
+        for s in self.spatial_shape:
+            n *= s
+        return n
+
+    def find_indice_pair(self, key):
+        if key is None:
+            return None
+        return self.indice_dict.get(key, None)
+
+
+class SparseModule(nn.Module):
+    """Marker base class (spconv.pytorch.modules.SparseModule; blocks.py:5,44)."""
+    pass
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BatchNorm folding (eval mode), cached per module and invalidated when any parameter/buffer changes
+# ---------------------------------------------------------------------------------------------------------
+_bn_cache = weakref.WeakKeyDictionary()
+
+
+def fold_bn(bn):
+    """-> (scale, shift) float32 CUDA tensors with y = x*scale + shift == BatchNorm1d(eval)(x)."""
+    if bn.training:
+        raise RuntimeError('softgroup_b200 sparse modules are inference-only: call model.eval() '
+                           '(BatchNorm1d in training mode cannot be folded)')
+    ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.weight.data_ptr(), bn.running_mean.data_ptr())
+    hit = _bn_cache.get(bn)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        inv = torch.rsqrt(bn.running_var.double() + bn.eps)
+        scale = bn.weight.double() * inv
+        shift = bn.bias.double() - bn.running_mean.double() * scale
+        scale, shift = scale.float().contiguous(), shift.float().contiguous()
+    _bn_cache[bn] = (ver, scale, shift)
+    return scale, shift
+
+
+def bn_relu_rows(x, scale, shift, relu):
+    """Standalone BatchNorm(eval)(+ReLU) over the rows of a dense [M,C] tensor."""
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    M, C = x.shape
+    with profiler.record('bn_relu', 8 * M * C):
+        check(_lib.lib().sgb_bn_relu(ptr(x), C, ptr(scale), ptr(shift), int(relu), ptr(y), C, M, C, _stream()),
+              'sgb_bn_relu')
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# rulebooks
+# ---------------------------------------------------------------------------------------------------------
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def _indices_i32(indices):
+    if indices.dtype != torch.int32:
+        indices = indices.int()
+    return indices.contiguous()
+
+
+def build_subm_map(indices):
+    L = _lib.lib()
+    indices = _indices_i32(indices)
+    M = indices.size(0)
+    mp = torch.empty((27, M), dtype=torch.int32, device=indices.device)
+    ws = _ws(L.sgb_rulebook_workspace_bytes(M), indices.device)
+    with profiler.record('rulebook_subm3', 16 * M + 4 * 27 * M):
+        check(L.sgb_rulebook_subm3(ptr(indices), M, ptr(mp), ptr(ws), ws.numel(), _stream()), 'sgb_rulebook_subm3')
+    return mp
+
+
+def build_down_map(indices, spatial_shape):
+    L = _lib.lib()
+    indices = _indices_i32(indices)
+    M = indices.size(0)
+    dev = indices.device
+    ws = _ws(L.sgb_rulebook_workspace_bytes(M), dev)
+    shp = (ctypes.c_int * 3)(*[int(s) for s in spatial_shape])
+    with profiler.record('rulebook_down2', 16 * M + 4 * 9 * M):
+        Mout = check(L.sgb_rulebook_down2_count(ptr(indices), M, shp, ptr(ws), ws.numel(), _stream()),
+                     'sgb_rulebook_down2_count')
+    out_indices = torch.empty((Mout, 4), dtype=torch.int32, device=dev)
+    mp = torch.empty((8, Mout), dtype=torch.int32, device=dev)
+    inv = torch.empty((8, M), dtype=torch.int32, device=dev)
+    check(
+        L.sgb_rulebook_down2_fill(ptr(indices), M, Mout, ptr(out_indices), ptr(mp), ptr(inv), ptr(ws), ws.numel(),
+                                  _stream()), 'sgb_rulebook_down2_fill')
+    return out_indices, mp, inv, [int(s) // 2 for s in spatial_shape]
+
+
+def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, residual=None, bias=None, out=None,
+                 out_stride=None, out_off=0):
+    """Thin wrapper over sgb_spconv_forward. W: [K, Cin, Cout] f32. act: (scale, shift) or None."""
+    if out is None:
+        out = torch.empty((Mout, Cout), dtype=torch.float32, device=feats.device)
+        out_stride = Cout
+    scale, shift = act if act is not None else (None, None)
+    rs, ro = (residual.stride(0), 0) if residual is not None else (0, 0)
+    # algorithmic bytes: input rows once + weights + map + output rows (+ residual)
+    m_in = feats.size(0)
+    nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
+    if residual is not None:
+        nbytes += 4 * Mout * Cout
+    with profiler.record('spconv_kernel' if mp is not None else 'spconv_kernel(1x1/linear)', nbytes):
+        check(
+            _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W), Cin, Cout,
+                                          ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
+                                          out_stride, out_off, _stream()), 'sgb_spconv_forward')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# convolution modules
+# ---------------------------------------------------------------------------------------------------------
+class _SparseConvBase(SparseModule):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, indice_key=None):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = [kernel_size] * 3 if isinstance(kernel_size, int) else list(kernel_size)
+        self.stride = [stride] * 3 if isinstance(stride, int) else list(stride)
+        self.padding = [padding] * 3 if isinstance(padding, int) else list(padding)
+        self.indice_key = indice_key
+        # spconv 2.x layout [out, k0, k1, k2, in] (tools/convert_checkpoint.py:17-19)
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self._wt = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=5**0.5)
+        if self.bias is not None:
+            fan_in = self.in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+            bound = 1 / fan_in**0.5
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def weight_kio(self):
+        """[K, Cin, Cout] contiguous copy of the weight, cached until the parameter changes."""
+        ver = (self.weight._version, self.weight.data_ptr(), self.weight.device)
+        if self._wt is None or self._wt[0] != ver:
+            with torch.no_grad():
+                w = self.weight.detach().reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0).contiguous()
+            self._wt = (ver, w.float())
+        return self._wt[1]
+
+    def _features(self, x):
+        f = x.features
+        assert f.is_cuda and f.dtype == torch.float32, 'softgroup_b200 sparse convs run on CUDA float32 features'
+        if f.stride(-1) != 1:
+            f = f.contiguous()
+        return f
+
+
+class SubMConv3d(_SparseConvBase):
+    """Submanifold 3x3x3 convolution (blocks.py:57-70, softgroup.py:61)."""
+
+    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0):
+        assert self.kernel_size == [3, 3, 3], 'only the k=3 submanifold conv of the reference is built'
+        f = self._features(x)
+        rb = x.find_indice_pair(self.indice_key)
+        if rb is None:
+            rb = {'kind': 'subm', 'map': build_subm_map(x.indices)}
+            if self.indice_key is not None:
+                x.indice_dict[self.indice_key] = rb
+        M = x.indices.size(0)
+        o = conv_forward(f, f.stride(0), 0, rb['map'], 27, M, self.weight_kio(), self.in_channels, self.out_channels,
+                         act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride, out_off=out_off)
+        return x.replace_feature(o)
+
+
+class SparseConv3d(_SparseConvBase):
+    """k=2 s=2 strided sparse conv (blocks.py:101-107) and, with kernel_size=1, the dense 1x1 (blocks.py:31-41)."""
+
+    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0):
+        f = self._features(x)
+        if self.kernel_size == [1, 1, 1]:
+            M = x.indices.size(0)
+            o = conv_forward(f, f.stride(0), 0, None, 1, M, self.weight_kio(), self.in_channels, self.out_channels,
+                             act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride,
+                             out_off=out_off)
+            return x.replace_feature(o)
+        assert self.kernel_size == [2, 2, 2] and self.stride == [2, 2, 2] and self.padding == [0, 0, 0], \
+            'only the k2 s2 p0 strided conv of the reference is built'
+        rb = x.find_indice_pair(self.indice_key)
+        if rb is None:
+            out_indices, mp, inv, out_shape = build_down_map(x.indices, x.spatial_shape)
+            rb = {'kind': 'down', 'map': mp, 'inv_map': inv, 'out_indices': out_indices, 'out_shape': out_shape,
+                  'in_indices': x.indices, 'in_shape': x.spatial_shape}
+            if self.indice_key is not None:
+                x.indice_dict[self.indice_key] = rb
+        Mout = rb['out_indices'].size(0)
+        o = conv_forward(f, f.stride(0), 0, rb['map'], 8, Mout, self.weight_kio(), self.in_channels, self.out_channels,
+                         act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride, out_off=out_off)
+        t = SparseConvTensor(o, rb['out_indices'], rb['out_shape'], x.batch_size, x.grid, x.indice_dict)
+        return t
+
+
+class SparseInverseConv3d(_SparseConvBase):
+    """Inverse of the k2 s2 conv with the same indice_key (blocks.py:114-119): restores its input sites and order."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key=None, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, bias=bias, indice_key=indice_key)
+
+    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0):
+        f = self._features(x)
+        rb = x.find_indice_pair(self.indice_key)
+        assert rb is not None and rb['kind'] == 'down', 'SparseInverseConv3d needs the pairs of indice_key %r' % (
+            self.indice_key, )
+        M = rb['in_indices'].size(0)
+        o = conv_forward(f, f.stride(0), 0, rb['inv_map'], 8, M, self.weight_kio(), self.in_channels,
+                         self.out_channels, act=act, residual=residual, bias=self.bias, out=out,
+                         out_stride=out_stride, out_off=out_off)
+        return SparseConvTensor(o, rb['in_indices'], rb['in_shape'], x.batch_size, x.grid, x.indice_dict)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SparseSequential with BN/ReLU -> conv peephole fusion
+# ---------------------------------------------------------------------------------------------------------
+class SparseSequential(SparseModule):
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        if len(args) == 1 and isinstance(args[0], OrderedDict):
+            for key, module in args[0].items():
+                self.add_module(key, module)
+        else:
+            for idx, module in enumerate(args):
+                self.add_module(str(idx), module)
+        for name, module in kwargs.items():
+            self.add_module(name, module)
+
+    def __getitem__(self, idx):
+        if not (-len(self) <= idx < len(self)):
+            raise IndexError('index {} is out of range'.format(idx))
+        if idx < 0:
+            idx += len(self)
+        return list(self._modules.values())[idx]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def add(self, module, name=None):
+        if name is None:
+            name = str(len(self._modules))
+        self.add_module(name, module)
+
+    @staticmethod
+    def _flush(x, pending):
+        scale, shift, relu = pending
+        if isinstance(x, SparseConvTensor):
+            return x.replace_feature(bn_relu_rows(x.features, scale, shift, relu))
+        return bn_relu_rows(x, scale, shift, relu)
+
+    def forward(self, input, residual=None, out=None, out_stride=None, out_off=0):
+        """residual / out* apply to the LAST sparse conv of the sequence (fused epilogue)."""
+        mods = list(self._modules.values())
+        last_conv = max([i for i, m in enumerate(mods) if isinstance(m, _SparseConvBase)], default=-1)
+        pending = None  # (scale, shift, relu)
+        x = input
+        for i, m in enumerate(mods):
+            is_sparse_in = isinstance(x, SparseConvTensor)
+            feats = x.features if is_sparse_in else x
+            fusable = feats.is_cuda and feats.dtype == torch.float32
+            if isinstance(m, nn.BatchNorm1d) and fusable and not m.training:
+                if pending is not None:
+                    x = self._flush(x, pending)
+                s, b = fold_bn(m)
+                pending = (s, b, False)
+                continue
+            if isinstance(m, nn.ReLU) and pending is not None and not pending[2]:
+                pending = (pending[0], pending[1], True)
+                continue
+            if isinstance(m, _SparseConvBase):
+                act = None
+                if pending is not None:
+                    if pending[2]:
+                        act = (pending[0], pending[1])
+                    else:  # BN without ReLU in front of a conv: not fusable into the relu'd input transform
+                        x = self._flush(x, pending)
+                    pending = None
+                if i == last_conv:
+                    x = m(x, act=act, residual=residual, out=out, out_stride=out_stride, out_off=out_off)
+                else:
+                    x = m(x, act=act)
+                continue
+            if pending is not None:
+                x = self._flush(x, pending)
+                pending = None
+            if isinstance(m, SparseModule):
+                x = m(x)
+            elif isinstance(x, SparseConvTensor):
+                if isinstance(m, nn.Identity):
+                    continue
+                if x.indices.shape[0] != 0:
+                    x = x.replace_feature(m(x.features))
+            else:
+                x = m(x)
+        if pending is not None:
+            x = self._flush(x, pending)
+        return x

@@ -1,0 +1,149 @@
+"""GPU parity: rulebooks (bit-exact) and sparse convolutions (fp32, within 1e-4 relative -- the north-star bar)
+against oracle/spconv_oracle.py, whose semantics are anchored on dense torch convs in tests/test_spconv_oracle.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spconv_oracle as so
+from softgroup_b200 import spconv, synth
+from softgroup_b200.configs import model_cfg
+from softgroup_b200.model import SoftGroup
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _case(seed, shape=(23, 18, 15), B=2, C=8, density=0.2):
+    rng = np.random.RandomState(seed)
+    idx = []
+    for b in range(B):
+        occ = np.argwhere(rng.rand(*shape) < density)
+        idx.append(np.concatenate([np.full((len(occ), 1), b), occ], 1))
+    idx = np.concatenate(idx, 0).astype(np.int32)
+    idx = idx[rng.permutation(len(idx))]
+    return idx, rng.randn(len(idx), C).astype(np.float32), shape, B
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def test_rulebook_subm3_bitexact():
+    idx, _, _, _ = _case(0)
+    mp = spconv.build_subm_map(_cuda(idx)).cpu().numpy()
+    assert np.array_equal(mp, so.subm_map(idx))
+
+
+@pytest.mark.parametrize('shape', [(23, 18, 15), (16, 16, 16), (9, 33, 7)])
+def test_rulebook_down2_bitexact(shape):
+    idx, _, shape, _ = _case(1, shape=shape)
+    out_idx, mp, inv, oshape = spconv.build_down_map(_cuda(idx), shape)
+    o_idx, o_mp, o_inv, o_shape = so.down_map(idx, shape)
+    assert oshape == o_shape
+    assert np.array_equal(out_idx.cpu().numpy(), o_idx)
+    assert np.array_equal(mp.cpu().numpy(), o_mp)
+    assert np.array_equal(inv.cpu().numpy(), o_inv)
+
+
+def test_rulebook_full_size():
+    scan = synth.make_scan('c2_scannet', seed=0)
+    import oracle
+    vc, _, _ = oracle.voxelization_idx(scan['coords'], 1, 4)
+    idx = vc.astype(np.int32)
+    mp = spconv.build_subm_map(_cuda(idx)).cpu().numpy()
+    assert np.array_equal(mp, so.subm_map(idx))
+    out_idx, dmp, inv, _ = spconv.build_down_map(_cuda(idx), scan['spatial_shape'])
+    o_idx, o_mp, o_inv, _ = so.down_map(idx, scan['spatial_shape'])
+    assert np.array_equal(out_idx.cpu().numpy(), o_idx) and np.array_equal(dmp.cpu().numpy(), o_mp)
+    assert np.array_equal(inv.cpu().numpy(), o_inv)
+
+
+@pytest.mark.parametrize('Cin,Cout', [(6, 32), (32, 32), (64, 32), (96, 128), (16, 48), (224, 224)])
+def test_subm_conv_vs_oracle(Cin, Cout):
+    idx, feats, _, _ = _case(Cin + Cout, C=Cin, density=0.25)
+    rng = np.random.RandomState(2)
+    W = (rng.randn(Cout, 3, 3, 3, Cin) / np.sqrt(27 * Cin)).astype(np.float32)
+    conv = spconv.SubMConv3d(Cin, Cout, 3, padding=1, bias=False, indice_key='k').cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(W))
+        x = spconv.SparseConvTensor(_cuda(feats), _cuda(idx), (23, 18, 15), 2)
+        y = conv(x)
+    want = so.subm_conv3d(feats, idx, W, acc64=True)
+    assert _rel(y.features.cpu().numpy(), want) < 2e-6
+    assert 'k' in x.indice_dict
+
+
+def test_conv_fused_act_residual_bias_strided():
+    idx, feats, _, _ = _case(5, C=40)
+    rng = np.random.RandomState(3)
+    M = len(idx)
+    W = (rng.randn(24, 3, 3, 3, 40) / 30).astype(np.float32)
+    scale, shift = rng.rand(40).astype(np.float32) + 0.5, rng.randn(40).astype(np.float32) * 0.3
+    res = rng.randn(M, 24).astype(np.float32)
+    bias = rng.randn(24).astype(np.float32)
+    mp = so.subm_map(idx)
+    wk = torch.from_numpy(W.reshape(24, 27, 40).transpose(1, 2, 0).copy()).cuda()
+    out = torch.full((M, 64), 7.0, device='cuda')
+    spconv.conv_forward(_cuda(feats), 40, 0, _cuda(mp), 27, M, wk, 40, 24, act=(_cuda(scale), _cuda(shift)),
+                        residual=_cuda(res), bias=_cuda(bias), out=out, out_stride=64, out_off=32)
+    act = np.maximum(feats * scale + shift, 0).astype(np.float32)
+    want = so.conv_from_map(act, mp, W, acc64=True) + res + bias
+    got = out.cpu().numpy()
+    assert _rel(got[:, 32:56], want) < 2e-6
+    assert np.all(got[:, :32] == 7.0) and np.all(got[:, 56:] == 7.0)
+
+
+def test_down_and_inverse_modules():
+    idx, feats, shape, B = _case(7, C=32)
+    rng = np.random.RandomState(4)
+    Wd = (rng.randn(64, 2, 2, 2, 32) / 16).astype(np.float32)
+    Wi = (rng.randn(32, 2, 2, 2, 64) / 8).astype(np.float32)
+    down = spconv.SparseConv3d(32, 64, 2, stride=2, bias=False, indice_key='sp').cuda()
+    inv = spconv.SparseInverseConv3d(64, 32, 2, bias=False, indice_key='sp').cuda()
+    with torch.no_grad():
+        down.weight.copy_(torch.from_numpy(Wd))
+        inv.weight.copy_(torch.from_numpy(Wi))
+        x = spconv.SparseConvTensor(_cuda(feats), _cuda(idx), shape, B)
+        y = down(x)
+        z = inv(y)
+    o, o_idx, o_inv, o_shape = so.sparse_conv3d_k2s2(feats, idx, shape, Wd, acc64=True)
+    assert np.array_equal(y.indices.cpu().numpy(), o_idx) and y.spatial_shape == o_shape
+    assert _rel(y.features.cpu().numpy(), o) < 2e-6
+    back = so.inverse_conv3d_k2(o, o_inv, Wi, acc64=True)
+    assert np.array_equal(z.indices.cpu().numpy(), idx)
+    assert _rel(z.features.cpu().numpy(), back) < 2e-6
+
+
+def _randomize_bn(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            with torch.no_grad():
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=g) * 0.4 + 0.8)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+@pytest.mark.parametrize('channels,num_blocks', [(16, 4), (32, 7)])
+def test_backbone_vs_oracle(channels, num_blocks):
+    """Whole sparse U-Net (53 SubM + 6 down + 6 inverse + 6 1x1 + 65 BN/ReLU at 32x7) vs the numpy restatement."""
+    import oracle
+    torch.manual_seed(0)
+    scan = synth.make_scan('c1_plumbing', seed=0, n_points=6000)
+    vc, v2p, p2v = oracle.voxelization_idx(scan['coords'], 1, 4)
+    feats = np.concatenate([scan['feats'], scan['coords_float']], 1).astype(np.float32)
+    vfeats = oracle.voxelization(feats, p2v, 4)
+    model = SoftGroup(**model_cfg('scannet', channels=channels, num_blocks=num_blocks)).cuda().eval()
+    _randomize_bn(model, 1)
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    want = so.backbone(vfeats, vc.astype(np.int32), scan['spatial_shape'], sd, channels, num_blocks, acc64=True)
+    with torch.no_grad():
+        x = spconv.SparseConvTensor(_cuda(vfeats), _cuda(vc.astype(np.int32)), scan['spatial_shape'], 1)
+        out = model.output_layer(model.unet(model.input_conv(x))).features.cpu().numpy()
+    assert out.shape == want.shape
+    assert _rel(out, want) < 1e-4  # north star: float features within 1e-4 relative
+    np.testing.assert_allclose(out, want, rtol=1e-3, atol=1e-4 * np.abs(want).max())
