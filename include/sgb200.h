@@ -188,6 +188,14 @@ int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const floa
 /* out[i, :] = in[index[i], :]  (the "devoxelize" gather of softgroup.py:374); index int32 [N]. */
 int sgb_gather_rows(const float *d_in, const int32_t *d_index, float *d_out, int N, int C, void *stream);
 
+/* Host-side serialisation of instance masks into the reference's RLE wire format (softgroup/util/rle.py:5-19:
+ * dict(length, counts='start len start len ...'), 1-based starts). h_ids: ascending point ids of all masks back to
+ * back (int32), h_offs int64 [n_masks+1]. Writes the `counts` strings back to back into h_out and their byte ranges
+ * into h_out_offs [n_masks+1]. Returns bytes written, or SGB_ERR_OVERFLOW if out_cap is too small
+ * (12 bytes per run + 2 always suffices). No CUDA involved. */
+long long sgb_rle_format_ids(const int32_t *h_ids, const long long *h_offs, int n_masks, char *h_out,
+                             long long out_cap, long long *h_out_offs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,20 +17,20 @@ model = SoftGroup(**model_cfg(cfgname)).cuda().eval()
 scan = synth.make_scan(shape, seed=0)
 hb = harness.to_host_batch(scan)
 t = time.time()
-print('calib', harness.calibrate_heads(model, hb), 'in %.2fs' % (time.time() - t))
+inj = harness.pointwise_injection(scan, sigma=float(sys.argv[2]) if len(sys.argv) > 2 else 0.03)
 model.profile_stages = True
 with torch.no_grad():
     for it in range(3):
         torch.cuda.synchronize()
         t = time.time()
-        ret = harness.run_scan(model, hb)
+        ret = harness.run_scan(model, hb, inject_pointwise=inj)
         torch.cuda.synchronize()
         dt = (time.time() - t) * 1e3
         print('iter %d: %.1f ms  stages %s' % (it, dt, {k: round(v, 2) for k, v in model.stage_ms.items()}))
-    ret = harness.run_scan(model, hb, device_only=True)
+    ret = harness.run_scan(model, hb, device_only=True, inject_pointwise=inj)
     po = ret['proposals_offset'].cpu().numpy()
     print('nProposal', len(po) - 1, 'sumNPoint', po[-1] if len(po) else 0, 'gt instances', len(scan['instance_pointnum']))
     if len(po) > 1:
         sz = np.diff(po)
         print('proposal sizes: min %d med %d max %d' % (sz.min(), np.median(sz), sz.max()))
-    print('pred_instances', len(harness.run_scan(model, hb)['pred_instances']))
+    print('nActive stats: see profiler'); print('pred_instances', len(harness.run_scan(model, hb, inject_pointwise=inj)['pred_instances']))

@@ -377,6 +377,41 @@ int sgb_voxelize_idx_cpu_finish(void *handle, const int64_t *h_coords, int64_t *
   return SGB_OK;
 }
 
+// ---- RLE wire format of the reference (softgroup/util/rle.py:5-19), host side ------------------------------
+// ids: ascending point ids of all masks back to back; offs [n_masks+1]; writes "start len start len ..." (1-based
+// starts) per mask into out, out_offs [n_masks+1] = byte ranges. Returns bytes written or SGB_ERR_OVERFLOW.
+long long sgb_rle_format_ids(const int32_t *h_ids, const long long *h_offs, int n_masks, char *h_out,
+                             long long out_cap, long long *h_out_offs) {
+  auto put = [](char *p, long long v) -> char * {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+  };
+  char *p = h_out;
+  char *end = h_out + out_cap;
+  for (int m = 0; m < n_masks; m++) {
+    h_out_offs[m] = p - h_out;
+    long long a = h_offs[m], b = h_offs[m + 1];
+    bool first = true;
+    long long i = a;
+    while (i < b) {
+      long long j = i + 1;
+      while (j < b && h_ids[j] == h_ids[j - 1] + 1) j++;
+      if (end - p < 48) { set_error("sgb_rle_format_ids: output buffer too small"); return SGB_ERR_OVERFLOW; }
+      if (!first) *p++ = ' ';
+      p = put(p, (long long)h_ids[i] + 1);
+      *p++ = ' ';
+      p = put(p, j - i);
+      first = false;
+      i = j;
+    }
+  }
+  h_out_offs[n_masks] = p - h_out;
+  return p - h_out;
+}
+
 int sgb_voxelize_fp(const float *d_feats, float *d_out, const int32_t *d_rules, int mode, int M, int maxActive, int C,
                     void *stream) {
   if (M == 0 || C == 0) return SGB_OK;

@@ -38,14 +38,21 @@ def h2d_bytes(batch):
     return int(sum(v.numel() * v.element_size() for v in batch.values() if isinstance(v, torch.Tensor)))
 
 
-def run_scan(model, host_batch, device_only=False):
+def pointwise_injection(scan, sigma=0.03, seed=0, logit=8.0):
+    """Device-resident synthetic point-wise predictions (see SoftGroup.forward_test `inject_pointwise`)."""
+    from . import synth
+    scores, off = synth.grouping_inputs(scan, sigma=sigma, seed=seed, logit=logit)
+    return torch.from_numpy(scores).cuda(), torch.from_numpy(off).cuda()
+
+
+def run_scan(model, host_batch, device_only=False, inject_pointwise=None):
     """End-to-end call a user makes: pinned host tensors in, result dict out. Point->voxel hashing runs on the GPU
     (voxelization_idx with CUDA tensors), then SoftGroup.forward_test."""
     dev = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     voxel_coords, v2p_map, p2v_map = ops.voxelization_idx(dev['coords'], dev['batch_size'])
     dev.update(voxel_coords=voxel_coords, v2p_map=v2p_map, p2v_map=p2v_map)
     dev.pop('coords')
-    return model.forward_test(device_only=device_only, **dev)
+    return model.forward_test(device_only=device_only, inject_pointwise=inject_pointwise, **dev)
 
 
 def device_batch(host_batch):

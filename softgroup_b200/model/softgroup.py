@@ -144,6 +144,13 @@ class SoftGroup(nn.Module):
         assert not lvl_fusion, 'lvl_fusion (SoftGroup++) is not built yet'
         semantic_scores, pt_offsets, output_feats = self.forward_backbone(input, v2p_map, x4_split=x4_split)
         self._mark('backbone')
+        inject = kwargs.get('inject_pointwise', None)
+        if inject is not None:
+            # bench/test hook (SURVEY.md 8d fallback, DESIGN.md "Synthetic workload"): a random-init backbone cannot
+            # produce trained-quality point-wise predictions, so the heads' outputs -- already computed above at full
+            # cost -- are overwritten by synthetic ones (one-hot*logit + N(0,1), centroid offsets + N(0,sigma)) to
+            # give the grouping stage the load a trained checkpoint would. Never used by the drop-in forward.
+            semantic_scores, pt_offsets = inject
         if x4_split:
             coords_float = self.merge_4_parts(coords_float)
             semantic_labels = self.merge_4_parts(semantic_labels)
@@ -392,38 +399,36 @@ class SoftGroup(nn.Module):
             keep[:, i] = False
         if device_only:
             return dict(keep=keep, score=score, npoint=npoint, on=on)
+        from ..util import rle_encode_many
+        # sort every proposal's points once (proposals_idx is in BFS order; RLE needs ascending ids)
+        pt_all = proposals_idx[:, 1].long()
+        order = torch.argsort(pid * num_points + pt_all)
+        pid_s, pt_s = pid[order], pt_all[order]
+        sel = on[order].t() & keep.t()[:, pid_s]  # [nI, sumNPoint]; row-major nonzero = class-major, proposal, pt
+        ci, pos = sel.nonzero(as_tuple=True)
+        ids = pt_s[pos].int()
+        inst_key = ci * num_instances + pid_s[pos]
+        counts = torch.bincount(inst_key, minlength=nI * num_instances)
+        kc, kp = keep.t().nonzero(as_tuple=True)  # kept (class, proposal) pairs, class-major
+        conf = score.t()[kc, kp]
+        cnt_kept = counts[kc * num_instances + kp]
+        ids_np = ids.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(cnt_kept.cpu().numpy().astype(np.int64))])
+        kc_np, conf_np = kc.cpu().numpy(), conf.cpu().numpy()
+        rles = rle_encode_many(ids_np, offs, num_points)
         instances = []
         semantic_pred = None
-        keep_t = keep.t().contiguous()  # class-major
-        kc, kp = keep_t.nonzero(as_tuple=True)
-        conf = score.t()[kc, kp]
-        # (class, proposal) -> rank among kept instances; expand to the points of kept masks
-        rank = torch.full((nI, num_instances), -1, dtype=torch.long, device=on.device)
-        rank[kc, kp] = torch.arange(kc.numel(), device=on.device)
-        pr = rank[:, pid].t()  # [sumNPoint, nI] rank of (class i, proposal of this point)
-        sel = on & (pr >= 0)
-        rows, cols = sel.nonzero(as_tuple=True)
-        inst_rank = pr[rows, cols]
-        pt = proposals_idx[:, 1].long()[rows]
-        order = torch.argsort(inst_rank * num_points + pt)
-        inst_rank, pt = inst_rank[order], pt[order]
-        counts = torch.bincount(inst_rank, minlength=kc.numel())
-        pt_np = pt.cpu().numpy()
-        counts_np = counts.cpu().numpy()
-        kc_np, conf_np = kc.cpu().numpy(), conf.cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(counts_np)])
         k = 0
         for i in range(nI):
             if i in self.sem2ins_classes:
                 if semantic_pred is None:
                     semantic_pred = semantic_scores.max(1)[1]
-                ids = (semantic_pred == i).nonzero().view(-1).cpu().numpy()
+                ids_i = (semantic_pred == i).nonzero().view(-1).cpu().numpy()
                 instances.append(dict(scan_id=scan_id, label_id=i + 1, conf=np.float32(1.),
-                                      pred_mask=rle_encode_ids(ids, num_points)))
+                                      pred_mask=rle_encode_ids(ids_i, num_points)))
                 continue
             while k < kc_np.size and kc_np[k] == i:
-                instances.append(dict(scan_id=scan_id, label_id=i + 1, conf=conf_np[k],
-                                      pred_mask=rle_encode_ids(pt_np[offs[k]:offs[k + 1]], num_points)))
+                instances.append(dict(scan_id=scan_id, label_id=i + 1, conf=conf_np[k], pred_mask=rles[k]))
                 k += 1
         return instances
 

@@ -49,6 +49,7 @@ SIGNATURES = {
                                    _P, c_int, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    'sgb_rle_format_ids': (c_longlong, [_P, _P, c_int, _P, c_longlong, _P]),
 }
 
 _lib = None

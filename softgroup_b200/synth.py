@@ -86,14 +86,19 @@ def make_scan(shape='c2_scannet', seed=0, n_points=None, batch_id=0):
     pos = 0
     for (o, eu, ev, c, k), m in zip(surfaces, counts):
         uv = rng.rand(m, 2)
+        strips = max(1, int(np.sqrt(m) / 4))
+        uv = uv[np.lexsort((uv[:, 1], np.floor(uv[:, 0] * strips)))]
         xyz[pos:pos + m] = o + uv[:, :1] * eu + uv[:, 1:] * ev
         sem[pos:pos + m] = c
         inst[pos:pos + m] = k
         pos += m
     xyz += rng.randn(n, 3) * 0.003
-    # interleave surfaces so that point order is not trivially sorted by object (ScanNet vertex order is
-    # spatially coherent but not grouped); a fixed-stride shuffle keeps some locality.
-    perm = rng.permutation(n)
+    # Point order: ScanNet vertex order is spatially coherent (mesh chunks) but not grouped by object. Emulate it:
+    # every surface is rastered in strips, then the cloud is cut into blocks of 64 consecutive points and the
+    # blocks are shuffled.
+    blk = 64
+    nb = (n + blk - 1) // blk
+    perm = np.concatenate([np.arange(b * blk, min((b + 1) * blk, n)) for b in rng.permutation(nb)])
     xyz, sem, inst = xyz[perm], sem[perm], inst[perm]
 
     palette = rng.uniform(-0.8, 0.8, (cfg['sem'], 3))

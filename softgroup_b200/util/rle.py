@@ -34,3 +34,25 @@ def rle_decode(rle):
     for lo, n in zip(starts, nums):
         mask[lo:lo + n] = 1
     return mask
+
+
+def rle_encode_many(ids, offs, length):
+    """Batch version through the library's host formatter: ids int32 (ascending inside each mask, masks back to
+    back), offs int64 [n+1] -> list of rle dicts."""
+    import ctypes
+    from ..ops import _lib
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    n = offs.size - 1
+    if n <= 0:
+        return []
+    cap = int(ids.size) * 24 + 64 * n + 64
+    out = np.empty(cap, dtype=np.uint8)
+    out_offs = np.empty(n + 1, dtype=np.int64)
+    _lib.check(
+        _lib.lib().sgb_rle_format_ids(ids.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p), n,
+                                      out.ctypes.data_as(ctypes.c_void_p), cap,
+                                      out_offs.ctypes.data_as(ctypes.c_void_p)), 'sgb_rle_format_ids')
+    buf = out.tobytes()
+    o = out_offs.tolist()
+    return [dict(length=length, counts=buf[o[k]:o[k + 1]].decode('ascii')) for k in range(n)]
