@@ -182,16 +182,16 @@ int sgb_spconv_forward(const float *d_in, int in_stride, int in_off, const int32
                        int out_stride, int out_off, void *stream);
 
 /* Tensor-core version of sgb_spconv_forward (tcgen05.mma kind::tf32 with TMEM accumulators; 3xTF32 error-compensated
- * split so results are fp32-grade). Same semantics; weights come pre-split and pre-packed:
- *   N = Cout rounded up to 16 (<= 256), nkc = ceil(Cin/32);
- *   Whi/Wlo f32 [K][nkc][8][N][4]: element (k, kc, q, n, e) = part(W[k][32*kc + 4*q + e][n]) (0 outside Cin/Cout),
- *   hi = W with the low 13 mantissa bits cleared, lo = W - hi.
- * sgb_spconv_tc_packed_floats returns the length of each packed array. */
+ * split so results are fp32-grade). Same semantics; weights come pre-split and pre-packed in ONE array:
+ *   N = Cout rounded up to 16 (<= 256), nkc = ceil(Cin/32), Cin <= 256;
+ *   Wp f32 [K][nkc][8][2][N][4]: element (k, kc, q, part, n, e) = part(W[k][32*kc + 4*q + e][n]) (0 outside Cin/Cout),
+ *   part 0 = hi = W with the low 13 mantissa bits cleared (TF32-exact), part 1 = lo = W - hi.
+ * sgb_spconv_tc_packed_floats returns the length of the packed array. */
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout);
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
-                          const float *d_Whi, const float *d_Wlo, int Cin, int Cout, const float *d_in_scale,
-                          const float *d_in_shift, const float *d_residual, int res_stride, int res_off,
-                          const float *d_bias, float *d_out, int out_stride, int out_off, void *stream);
+                          const float *d_Wp, int Cin, int Cout, const float *d_in_scale, const float *d_in_shift,
+                          const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
+                          int out_stride, int out_off, void *stream);
 
 /* y[i, c] = max(x[i, c]*scale[c] + shift[c], 0) (relu != 0) -- BatchNorm1d(eval)+ReLU over rows. */
 int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const float *d_shift, int relu, float *d_y,

@@ -22,19 +22,19 @@ namespace sgb {
 
 constexpr int TC_ROWS = 128;
 constexpr int TC_KC = 32;  // channels per stage
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 320;  // 8 producer warps + 1 MMA warp + 1 weight-loader warp
 
 struct TcArgs {
   const float *in; int in_stride, in_off;
   const int32_t *map; int K, Mout;
-  const float *Whi, *Wlo;  // packed [K][nkc][8][N][4]
+  const float *Wp;  // packed [K][nkc][8 chunks][2 (hi,lo)][N][4]
   int Cin, N, Cout;        // N = Cout rounded up to 16
   int NT;                  // columns per CTA (multiple of 16); gridDim.y = ceil(N / NT)
   const float *in_scale, *in_shift;
   const float *residual; int res_stride, res_off;
   const float *bias;
   float *out; int out_stride, out_off;
-  int nstages, tmem_cols;
+  int nstages, nbstages, tmem_cols;  // A ring depth, B (weight) ring depth
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,30 +84,56 @@ __device__ __forceinline__ float4 tf32_hi(float4 v) {
   return h;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+// Warp roles: warps 0-3 = producer group 0, warps 4-7 = producer group 1 (one output row per thread; the groups
+// take alternate pipeline iterations), warp 8 = MMA issuer (one elected lane). Producers keep the NEXT iteration's
+// gathered row slice in registers while the current one is being split and stored, so the L2 latency of the gather
+// overlaps the stores, the weight copy (cp.async) and the other group's work. full[s]: 128 producer arrivals,
+// free[s]: tcgen05.commit, done: accumulator complete.
 __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bars[8];  // [0..3] stage free, [4] accumulator done
+  __shared__ __align__(8) unsigned long long bars[20];  // [0..3] A full, [4..7] A free, [8] done, [10..14] B full, [15..19] B free
   __shared__ uint32_t s_tmem;
+  __shared__ unsigned int s_mask;
+  __shared__ int s_list[32];
+  __shared__ int s_nact;
+  __shared__ __align__(16) float s_scale[512], s_shift[512];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & (TC_ROWS - 1), half = tid >> 7;  // two threads per row: each gathers 16 of the 32 channels
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp < 8;
+  const int grp = warp >> 2;          // producer group (0/1)
+  const int r = tid & (TC_ROWS - 1);  // row of this producer thread
   const int row0 = blockIdx.x * TC_ROWS;
   const int my_row = row0 + r;
-  const bool row_ok = my_row < p.Mout;
+  const bool row_ok = producer && my_row < p.Mout;
   const bool has_act = p.in_scale != nullptr;
   const bool vec_ok = ((p.in_stride & 3) == 0) && ((p.in_off & 3) == 0) && ((((uintptr_t)p.in) & 15) == 0);
   const int N = p.N, NT = p.NT;
   const int n0 = blockIdx.y * NT;
-  const int nt = min(NT, N - n0);                       // columns of this CTA (multiple of 16)
-  const uint32_t a_bytes = TC_ROWS * TC_KC * 4;         // 16 KB
-  const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;    // NT * 128 B
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const int NS = p.nstages;
+  const int nt = min(NT, N - n0);                     // columns of this CTA (multiple of 16)
+  const uint32_t a_bytes = TC_ROWS * TC_KC * 4;       // 16 KB
+  const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;  // NT * 128 B
+  const uint32_t stage_bytes = 2 * a_bytes;     // A ring stage: hi + lo
+  const uint32_t bstage_bytes = 2 * b_bytes;    // B ring stage: hi + lo
+  const int NS = p.nstages, NSB = p.nbstages;
+  unsigned char *bring = smem + (size_t)NS * stage_bytes;
+  int32_t *map_s = reinterpret_cast<int32_t *>(bring + (size_t)NSB * bstage_bytes);  // [K][128] (only when p.map)
 
   if (tid == 0) {
-    for (int i = 0; i < NS; i++) mbar_init(smem_u32(&bars[i]), 1);
-    mbar_init(smem_u32(&bars[4]), 1);
+    for (int i = 0; i < NS; i++) {
+      mbar_init(smem_u32(&bars[i]), TC_ROWS);
+      mbar_init(smem_u32(&bars[4 + i]), 1);
+    }
+    mbar_init(smem_u32(&bars[8]), 1);
+    for (int i = 0; i < NSB; i++) {
+      mbar_init(smem_u32(&bars[10 + i]), 1);
+      mbar_init(smem_u32(&bars[15 + i]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_mask = 0u;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -119,123 +145,217 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
-  // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3, M>>4
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
 
+  if (has_act) {
+    for (int c = tid; c < 512; c += TC_THREADS) {
+      s_scale[c] = (c < p.Cin) ? __ldg(&p.in_scale[c]) : 0.f;
+      s_shift[c] = (c < p.Cin) ? __ldg(&p.in_shift[c]) : 0.f;
+    }
+  }
+  // ---- rulebook slice of this tile -> shared memory; which kernel offsets have any active pair ------------
+  if (p.map) {
+    unsigned int flags = 0u;
+    if (producer) {
+      for (int o = grp; o < p.K; o += 2) {
+        int src = row_ok ? __ldg(&p.map[(size_t)o * p.Mout + my_row]) : -1;
+        map_s[o * TC_ROWS + r] = src;
+        if (src >= 0) flags |= 1u << o;
+      }
+    }
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(&s_mask, flags);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    if (p.map) {
+      unsigned int m = s_mask;
+      for (int o = 0; o < p.K; o++)
+        if (m >> o & 1u) s_list[n++] = o;
+    } else {
+      s_list[n++] = 0;
+    }
+    s_nact = n;
+  }
+  __syncthreads();
   const int nkc = (p.Cin + TC_KC - 1) / TC_KC;
-  int it = 0;
-  int src_next = -1;
-  if (row_ok) src_next = p.map ? __ldg(&p.map[my_row]) : my_row;
-  for (int o = 0; o < p.K; o++) {
-    const int src = src_next;
-    if (o + 1 < p.K && row_ok) src_next = __ldg(&p.map[(size_t)(o + 1) * p.Mout + my_row]);  // prefetch
-    if (!__syncthreads_or(src >= 0)) continue;
-    for (int kc = 0; kc < nkc; kc++, it++) {
-      const int s = it % NS;
-      if (it >= NS) mbar_wait(smem_u32(&bars[s]), (uint32_t)((it / NS - 1) & 1));
+  const int total = s_nact * nkc;
+
+  if (producer) {
+    float4 v[8];
+    int vsrc = -1;
+    // gather of iteration i into registers (whole 32-channel slice of this thread's row)
+    auto load_iter = [&](int a_idx, int kc) {
+      const int o = s_list[a_idx];
+      const int c0 = kc * TC_KC;
+      const int kvalid = min(TC_KC, p.Cin - c0);
+      vsrc = p.map ? map_s[o * TC_ROWS + r] : (row_ok ? my_row : -1);
+      const float *rp = (vsrc >= 0) ? p.in + (size_t)vsrc * p.in_stride + p.in_off + c0 : nullptr;
+      const bool fast = (vsrc >= 0) && vec_ok && (kvalid == TC_KC);
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fast) {
+          v[q] = __ldg(reinterpret_cast<const float4 *>(rp) + q);
+        } else if (vsrc >= 0 && 4 * q < kvalid) {
+          float t[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) t[e] = (4 * q + e < kvalid) ? __ldg(rp + 4 * q + e) : 0.f;
+          v[q] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+    };
+    // iteration i = grp, grp+2, ...: (a_idx, kc) = (i / nkc, i % nkc), stage s = i % NS, use u = i / NS -- all advanced
+    // incrementally (no integer division in the loop)
+    int i = grp;
+    int kc = grp, a_idx = 0;
+    while (kc >= nkc) { kc -= nkc; a_idx++; }
+    int s = grp % NS, u = grp / NS;
+    if (i < total) load_iter(a_idx, kc);
+    for (; i < total; i += 2) {
+      if (u >= 1) mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((u - 1) & 1));
       unsigned char *st = smem + (size_t)s * stage_bytes;
       float4 *Ahi = reinterpret_cast<float4 *>(st);
       float4 *Alo = reinterpret_cast<float4 *>(st + a_bytes);
-      float4 *Bhi = reinterpret_cast<float4 *>(st + 2 * a_bytes);
-      float4 *Blo = reinterpret_cast<float4 *>(st + 2 * a_bytes + b_bytes);
       const int c0 = kc * TC_KC;
-      const int kvalid = min(TC_KC, p.Cin - c0);  // channels of this slice that exist
+      const int kvalid = min(TC_KC, p.Cin - c0);
       const int ksteps = (kvalid + 7) >> 3;
-      // ---- B: packed weight slice (already split, core-matrix order) via cp.async -----------------------
-      {
-        const size_t slice = ((size_t)o * nkc + kc) * (size_t)N * 8;  // float4 units: 8 chunks x N rows
-        const float4 *gh = reinterpret_cast<const float4 *>(p.Whi) + slice + n0;
-        const float4 *gl = reinterpret_cast<const float4 *>(p.Wlo) + slice + n0;
-        const int nvec = 2 * ksteps * nt;
-        const uint32_t bh = smem_u32(Bhi), bl = smem_u32(Blo);
-        for (int t = tid; t < nvec; t += TC_THREADS) {
-          int q = t / nt, n = t - q * nt;
-          cp_async16(bh + (uint32_t)(q * nt + n) * 16, gh + (size_t)q * N + n);
-          cp_async16(bl + (uint32_t)(q * nt + n) * 16, gl + (size_t)q * N + n);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      // ---- A: gathered row slice (this thread: chunks half*4 .. half*4+3) -> hi / lo core matrices -----
-      {
-        float4 v[4];
-        const float *rp = (src >= 0) ? p.in + (size_t)src * p.in_stride + p.in_off + c0 : nullptr;
-        const bool fast = (src >= 0) && vec_ok && (kvalid == TC_KC);
+      // ---- A: registers -> (BN+ReLU) -> hi / lo core matrices ---------------------------------------------
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int q = half * 4 + j;
-          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (fast) {
-            v[j] = __ldg(reinterpret_cast<const float4 *>(rp) + q);
-          } else if (src >= 0 && 4 * q < kvalid) {
-            float t[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) t[e] = (4 * q + e < kvalid) ? __ldg(rp + 4 * q + e) : 0.f;
-            v[j] = make_float4(t[0], t[1], t[2], t[3]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int q = half * 4 + j;
-          if (q < 2 * ksteps) {
-            float4 x = v[j];
-            if (has_act && src >= 0) {
-              float sc[4], sh[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                bool ok = 4 * q + e < kvalid;
-                sc[e] = ok ? __ldg(&p.in_scale[c0 + 4 * q + e]) : 0.f;
-                sh[e] = ok ? __ldg(&p.in_shift[c0 + 4 * q + e]) : 0.f;
-              }
-              x.x = fmaxf(fmaf(x.x, sc[0], sh[0]), 0.f);
-              x.y = fmaxf(fmaf(x.y, sc[1], sh[1]), 0.f);
-              x.z = fmaxf(fmaf(x.z, sc[2], sh[2]), 0.f);
-              x.w = fmaxf(fmaf(x.w, sc[3], sh[3]), 0.f);
+      for (int q = 0; q < 8; q++) {
+        if (q < 2 * ksteps) {
+          float4 x = v[q];
+          if (has_act && vsrc >= 0) {
+            const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[c0 + 4 * q]);
+            const float4 sh = *reinterpret_cast<const float4 *>(&s_shift[c0 + 4 * q]);
+            x.x = fmaxf(fmaf(x.x, sc.x, sh.x), 0.f);
+            x.y = fmaxf(fmaf(x.y, sc.y, sh.y), 0.f);
+            x.z = fmaxf(fmaf(x.z, sc.z, sh.z), 0.f);
+            x.w = fmaxf(fmaf(x.w, sc.w, sh.w), 0.f);
+            if (kvalid < TC_KC) {  // channels past Cin must stay exactly 0
+              if (4 * q + 0 >= kvalid) x.x = 0.f;
+              if (4 * q + 1 >= kvalid) x.y = 0.f;
+              if (4 * q + 2 >= kvalid) x.z = 0.f;
+              if (4 * q + 3 >= kvalid) x.w = 0.f;
             }
-            float4 h = tf32_hi(x);
-            float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-            Ahi[q * TC_ROWS + r] = h;  // chunk q, row r: byte offset q*2048 + r*16
-            Alo[q * TC_ROWS + r] = l;
           }
+          float4 h = tf32_hi(x);
+          float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          Ahi[q * TC_ROWS + r] = h;  // chunk q, row r: byte offset q*2048 + r*16
+          Alo[q * TC_ROWS + r] = l;
         }
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const int s_done = s;
+      kc += 2;
+      while (kc >= nkc) { kc -= nkc; a_idx++; }
+      s += 2;
+      if (s >= NS) { s -= NS; u++; }
+      if (i + 2 < total) load_iter(a_idx, kc);  // next gather of this group is in flight during the waits below
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo), b_hi = smem_u32(Bhi), b_lo = smem_u32(Blo);
-        const uint32_t a_lbo = TC_ROWS * 16, b_lbo = (uint32_t)nt * 16;
-        for (int ks = 0; ks < ksteps; ks++) {
-          uint64_t dah = umma_desc(a_hi + ks * 2 * a_lbo, a_lbo, 128);
-          uint64_t dal = umma_desc(a_lo + ks * 2 * a_lbo, a_lbo, 128);
-          uint64_t dbh = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
-          uint64_t dbl = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
-          umma_tf32(tmem, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem, dah, dbl, idesc, 1u);
-          umma_tf32(tmem, dal, dbh, idesc, 1u);
+      mbar_arrive(smem_u32(&bars[s_done]));
+    }
+  } else if (warp == 9) {
+    // ---- weight loader: one elected lane streams the packed slices with TMA bulk copies (cp.async.bulk, async proxy:
+    //      no generic->async fence needed) into a deeper ring; completion is signalled on the stage's mbarrier by
+    //      complete_tx. Global layout [chunk q][hi|lo][N][16 B] == shared layout [q][hi nt | lo nt][16 B] when the CTA
+    //      owns all N columns, so a whole slice is ONE bulk copy; with a column split it is one copy per (q, part).
+    if (lane == 0) {
+      int sb = 0, ub = 0, kc = 0, a_idx = 0;
+      for (int i = 0; i < total; i++) {
+        if (ub >= 1) mbar_wait(smem_u32(&bars[15 + sb]), (uint32_t)((ub - 1) & 1));
+        const int o = s_list[a_idx];
+        const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
+        const int ksteps = (kvalid + 7) >> 3;
+        const float4 *g = reinterpret_cast<const float4 *>(p.Wp) + ((size_t)o * nkc + kc) * (size_t)N * 16;
+        const uint32_t bb = smem_u32(bring + (size_t)sb * bstage_bytes);
+        const uint32_t bar = smem_u32(&bars[10 + sb]);
+        const int nseg = 4 * ksteps;  // (chunk, part) segments of nt*16 bytes
+        const uint32_t bytes = (uint32_t)nseg * (uint32_t)nt * 16u;
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+        if (nt == N) {
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(bb), "l"(g), "r"(bytes), "r"(bar) : "memory");
+        } else {
+          for (int j = 0; j < nseg; j++) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(bb + (uint32_t)(j * nt) * 16u), "l"(g + (size_t)j * N + n0), "r"((uint32_t)nt * 16u), "r"(bar)
+                         : "memory");
+          }
         }
-        umma_commit(smem_u32(&bars[s]));  // frees this stage once the MMAs above have read it
+        if (++sb == NSB) { sb = 0; ub++; }
+        if (++kc == nkc) { kc = 0; a_idx++; }
       }
     }
-  }
-  if (it > 0) {
-    if (tid == 0) umma_commit(smem_u32(&bars[4]));
-    mbar_wait(smem_u32(&bars[4]), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  } else if (warp == 8 && lane == 0) {
+    // ---- MMA issuer: per 8-channel k-step two instructions
+    //        D[:, 0:2nt]  += A_hi * [B_hi | B_lo]     (N = 2nt)
+    //        D[:, nt:2nt] += A_lo *  B_hi             (N = nt)
+    //      so columns [0,nt) hold hi*hi and [nt,2nt) the two correction products (summed in the epilogue).
+    //      Descriptors are advanced by adding constants to their low word; the issue loop is kept minimal because
+    //      a single thread's instruction stream paces the tensor pipe (measured ~50 cycles / tcgen05.mma at N<=64).
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * nt) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+    const uint32_t a_lbo = TC_ROWS * 16, b_lbo = (uint32_t)(2 * nt) * 16;
+    const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), b_step = (uint64_t)((2 * b_lbo) >> 4);
+    uint32_t first = 0u;  // 0 for the very first MMA (overwrite), then 1
+    int s = 0, sb = 0, kc = 0;
+    uint32_t pa = 0u, pb = 0u;
+    for (int i = 0; i < total; i++) {
+      mbar_wait(smem_u32(&bars[10 + sb]), pb);
+      mbar_wait(smem_u32(&bars[s]), pa);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
+      const int ksteps = (kvalid + 7) >> 3;
+      const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t sbt = smem_u32(bring + (size_t)sb * bstage_bytes);
+      uint64_t dah = umma_desc(st, a_lbo, 128);
+      uint64_t dal = umma_desc(st + a_bytes, a_lbo, 128);
+      uint64_t dbb = umma_desc(sbt, b_lbo, 128);
+      if (ksteps == 4) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          umma_tf32(tmem, dah, dbb, idesc2, (ks == 0) ? first : 1u);
+          umma_tf32(tmem + (uint32_t)nt, dal, dbb, idesc1, 1u);
+          dah += a_step; dal += a_step; dbb += b_step;
+        }
+      } else {
+        for (int ks = 0; ks < ksteps; ks++) {
+          umma_tf32(tmem, dah, dbb, idesc2, (ks == 0) ? first : 1u);
+          umma_tf32(tmem + (uint32_t)nt, dal, dbb, idesc1, 1u);
+          dah += a_step; dal += a_step; dbb += b_step;
+        }
+      }
+      first = 1u;
+      umma_commit(smem_u32(&bars[4 + s]));    // frees the A stage once the MMAs above have read it
+      umma_commit(smem_u32(&bars[15 + sb]));  // ... and the weight stage
+      if (++s == NS) { s = 0; pa ^= 1u; }
+      if (++sb == NSB) { sb = 0; pb ^= 1u; }
+      if (++kc == nkc) kc = 0;
+    }
+    if (total > 0) umma_commit(smem_u32(&bars[8]));
   }
   // ---- epilogue: TMEM lane = output row; warp w reads lanes 32*(w%4).., column half w/4 -----------------
-  {
+  if (producer) {
+    if (total > 0) {
+      mbar_wait(smem_u32(&bars[8]), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     const int lane_grp = warp & 3, chalf = warp >> 2;
-    const int row = row0 + lane_grp * 32 + (tid & 31);
+    const int row = row0 + lane_grp * 32 + lane;
     const int cbeg = chalf * (nt >> 1), cend = cbeg + (nt >> 1);
     for (int cb = cbeg; cb < cend; cb += 8) {
-      uint32_t v[8];
-      if (it > 0) {
+      uint32_t v[8], c[8];
+      if (total > 0) {
         uint32_t taddr = tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cb;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                      : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+                     : "r"(taddr + (uint32_t)nt));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(c[e]));
       } else {
 #pragma unroll
         for (int e = 0; e < 8; e++) v[e] = 0u;
@@ -273,25 +393,25 @@ extern "C" {
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout) {
   int N = (Cout + 15) / 16 * 16;
   int nkc = (Cin + 31) / 32;
-  return (long long)K * nkc * 8 * N * 4;
+  return (long long)K * nkc * 8 * 2 * N * 4;
 }
 
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
-                          const float *d_Whi, const float *d_Wlo, int Cin, int Cout, const float *d_in_scale,
+                          const float *d_Wp, int Cin, int Cout, const float *d_in_scale,
                           const float *d_in_shift, const float *d_residual, int res_stride, int res_off,
                           const float *d_bias, float *d_out, int out_stride, int out_off, void *stream) {
   if (Mout == 0 || Cout == 0) return SGB_OK;
-  SGB_REQUIRE(d_in && d_Whi && d_Wlo && d_out && K >= 1 && Mout > 0 && Cin > 0 && Cout > 0, SGB_ERR_ARG,
+  SGB_REQUIRE(d_in && d_Wp && d_out && K >= 1 && Mout > 0 && Cin > 0 && Cout > 0, SGB_ERR_ARG,
               "spconv_forward_tc arguments");
   SGB_REQUIRE(d_map || K == 1, SGB_ERR_ARG, "identity map requires K == 1");
   SGB_REQUIRE((d_in_scale == nullptr) == (d_in_shift == nullptr), SGB_ERR_ARG, "scale/shift must come together");
   SGB_REQUIRE(in_stride >= in_off + Cin && out_stride >= out_off + Cout, SGB_ERR_ARG, "row strides");
   int N = (Cout + 15) / 16 * 16;
-  SGB_REQUIRE(N <= 256, SGB_ERR_RANGE, "spconv_forward_tc: Cout > 256 is not tiled");
+  SGB_REQUIRE(N <= 256 && Cin <= 512, SGB_ERR_RANGE, "spconv_forward_tc: Cout > 256 or Cin > 512 is not tiled");
   TcArgs p;
   p.in = d_in; p.in_stride = in_stride; p.in_off = in_off;
   p.map = d_map; p.K = K; p.Mout = Mout;
-  p.Whi = d_Whi; p.Wlo = d_Wlo; p.Cin = Cin; p.N = N; p.Cout = Cout;
+  p.Wp = d_Wp; p.Cin = Cin; p.N = N; p.Cout = Cout;
   p.in_scale = d_in_scale; p.in_shift = d_in_shift;
   p.residual = d_residual; p.res_stride = res_stride; p.res_off = res_off;
   p.bias = d_bias;
@@ -299,22 +419,33 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   // Column split: few row tiles (deep U-Net levels) would leave most SMs idle and make one CTA stream all the
   // weights, so N is cut into NT-column CTAs until the grid covers the machine (NT multiple of 16, >= 32).
   int tiles = div_up(Mout, TC_ROWS);
-  int NT = N;
+  int NT = std::min(N, 128);  // [B_hi | B_lo] is one operand with 2*NT <= 256 columns
+  if (N > 128) NT = (N / 2 + 15) / 16 * 16;
   while (NT > 32 && tiles * div_up(N, NT) < kNumSMs) {
     int nxt = (NT / 2 + 15) / 16 * 16;
     if (nxt >= NT) break;
     NT = nxt;
   }
   p.NT = NT;
-  size_t stage = 2 * (size_t)TC_ROWS * TC_KC * 4 + 2 * (size_t)NT * TC_KC * 4;
-  p.nstages = (stage * 3 <= 110 * 1024) ? 3 : 2;
+  size_t stage = 2 * (size_t)TC_ROWS * TC_KC * 4;  // A ring stage (hi + lo)
+  size_t bstage = 2 * (size_t)NT * TC_KC * 4;      // weight ring stage (hi + lo)
+  size_t map_bytes = d_map ? (size_t)K * TC_ROWS * 4 : 0;
+  // two CTAs per SM (2 A stages + 4 weight stages) when that fits, else one CTA with deeper rings
+  p.nstages = 2;
+  p.nbstages = 4;
+  if (2 * (p.nstages * stage + p.nbstages * bstage + map_bytes + 2048) > 225 * 1024) {
+    p.nstages = 3;
+    size_t left = 210 * 1024 - map_bytes - p.nstages * stage;
+    p.nbstages = (int)std::max<size_t>(2, std::min<size_t>(4, left / bstage));
+    if (p.nbstages * bstage + p.nstages * stage + map_bytes > 210 * 1024) p.nstages = 2;
+  }
   int cols = 32;
-  while (cols < NT) cols <<= 1;
+  while (cols < 2 * NT) cols <<= 1;
   p.tmem_cols = cols;
-  size_t smem = stage * p.nstages + 1024;
+  size_t smem = stage * p.nstages + bstage * p.nbstages + map_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   dim3 grid(tiles, div_up(N, NT));
@@ -322,4 +453,66 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
+}
+
+// ---- micro-benchmark hook: cost of back-to-back tcgen05.mma kind::tf32 (M=128, N, K=8) into one accumulator ----
+namespace sgb {
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__global__ void umma_rate_kernel(int N, int reps, int per_commit, long long *out, int a_in_tmem) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 256 * 32 * 4) / 4; i += blockDim.x) reinterpret_cast<float *>(smem)[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+    uint64_t da = umma_desc(smem_u32(smem), 2048, 128);
+    uint64_t db = umma_desc(smem_u32(smem + 16384), (uint32_t)N * 16, 128);
+    long long t0 = clock64();
+    uint32_t phase = 0;
+    for (int r = 0; r < reps; r += per_commit) {
+      if (a_in_tmem > 0) {
+        for (int k = 0; k < per_commit; k++) umma_tf32_ts(tmem + 64 * (k % a_in_tmem), tmem + 256 + 8 * (k & 7), db, idesc, 1u);
+      } else {
+        for (int k = 0; k < per_commit; k++) umma_tf32(tmem + 64 * (k % (-a_in_tmem + 1)), da, db, idesc, 1u);
+      }
+      umma_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), phase);
+      phase ^= 1;
+    }
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+}  // namespace sgb
+
+extern "C" int sgb_test_umma_rate(int N, int reps, int per_commit, long long *d_out, void *stream, int a_in_tmem) {
+  SGB_CUDA_CHECK(cudaFuncSetAttribute(sgb::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  sgb::umma_rate_kernel<<<1, 128, 16384 + 256 * 32 * 4, (cudaStream_t)stream>>>(N, reps, per_commit, d_out, a_in_tmem);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
 }

@@ -143,30 +143,30 @@ CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores
 
 
 def pack_weight_tc(W):
-    """[K, Cin, Cout] f32 -> (Whi, Wlo) packed [K, nkc, 8, N, 4] for sgb_spconv_forward_tc (see sgb200.h)."""
+    """[K, Cin, Cout] f32 -> packed [K, nkc, 8, 2, N, 4] for sgb_spconv_forward_tc (layout in sgb200.h)."""
     K, Cin, Cout = W.shape
     N = (Cout + 15) // 16 * 16
     nkc = (Cin + 31) // 32
     Wp = torch.zeros((K, nkc * 32, N), dtype=torch.float32, device=W.device)
     Wp[:, :Cin, :Cout] = W
-    Wp = Wp.view(K, nkc, 8, 4, N).permute(0, 1, 2, 4, 3).contiguous()
+    Wp = Wp.view(K, nkc, 8, 4, N).permute(0, 1, 2, 4, 3).contiguous()  # [K, nkc, 8, N, 4]
     hi = (Wp.view(torch.int32) & -8192).view(torch.float32)  # clear the low 13 mantissa bits (TF32-exact)
     lo = Wp - hi
-    return hi.contiguous(), lo.contiguous()
+    return torch.stack([hi, lo], dim=3).contiguous()  # [K, nkc, 8, 2, N, 4]
 
 
 class WeightPack(object):
     """Weight of one conv in both kernel formats: .kio [K,Cin,Cout] and the packed tcgen05 split."""
-    __slots__ = ('kio', 'hi', 'lo')
+    __slots__ = ('kio', 'packed')
 
     def __init__(self, kio):
         self.kio = kio
-        self.hi = self.lo = None
+        self.packed = None
 
     def tc(self):
-        if self.hi is None:
-            self.hi, self.lo = pack_weight_tc(self.kio)
-        return self.hi, self.lo
+        if self.packed is None:
+            self.packed = pack_weight_tc(self.kio)
+        return self.packed
 
 
 def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, residual=None, bias=None, out=None,
@@ -185,15 +185,14 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    use_tc = CONV_IMPL == 'tc' and Cout <= 256
+    use_tc = CONV_IMPL == 'tc' and Cout <= 256 and Cin <= 256
     name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
     with profiler.record(name, nbytes):
         if use_tc:
-            hi, lo = W.tc()
             check(
-                _lib.lib().sgb_spconv_forward_tc(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(hi), ptr(lo), Cin,
-                                                 Cout, ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias),
-                                                 ptr(out), out_stride, out_off, _stream()), 'sgb_spconv_forward_tc')
+                _lib.lib().sgb_spconv_forward_tc(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.tc()), Cin, Cout,
+                                                 ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
+                                                 out_stride, out_off, _stream()), 'sgb_spconv_forward_tc')
         else:
             check(
                 _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.kio), Cin, Cout,
