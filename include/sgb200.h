@@ -103,7 +103,7 @@ int sgb_ballquery_batch_p_async(int n, long long capacity, float radius, const f
  * d_ball_query_idxs int32 [nActive], d_start_len int32 [N,2] (DEVICE memory; the reference takes CPU
  * tensors). threshold semantics (:70-82): a component is kept when (float)size >= thr, where the caller
  * passes thr = threshold if class_numpoint_mean[class_id] == -1 else threshold * mean.
- *   count (blocking): returns nCluster, writes sumNPoint to *h_sumNPoint.
+ *   count (blocking): returns nCluster, writes sumNPoint to *h_sumNPoint and the longest list length to *h_maxLen.
  *   fill: d_cluster_idxs int32 [sumNPoint,2] (cluster id, point idx), d_cluster_offsets int32 [nCluster+1].
  * Optional per-node segments (d_node_seg int32 [N], d_seg_thr f32 [nSeg]) give every node the threshold of
  * its segment (used to cluster all classes of a scan in one call); pass NULL for a single threshold.
@@ -113,10 +113,12 @@ int sgb_ballquery_batch_p_async(int n, long long capacity, float radius, const f
 size_t sgb_bfs_cluster_workspace_bytes(int N);
 int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, float thr,
                           const int32_t *d_node_seg, const float *d_seg_thr, int symmetric_hint, void *d_ws,
-                          size_t ws_bytes, int *h_sumNPoint, void *stream);
+                          size_t ws_bytes, int *h_sumNPoint, int *h_maxLen, void *stream);
+/* scratch for fill: one bitmap row of ceil(maxLen/32) words per emitted point (0 when maxLen > 2048: fallback path) */
+size_t sgb_bfs_cluster_scratch_bytes(int sumNPoint, int maxLen);
 int sgb_bfs_cluster_fill(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, int nCluster,
-                         int sumNPoint, int32_t *d_cluster_idxs, int32_t *d_cluster_offsets, void *d_ws,
-                         size_t ws_bytes, void *stream);
+                         int sumNPoint, int maxLen, int32_t *d_cluster_idxs, int32_t *d_cluster_offsets, void *d_ws,
+                         size_t ws_bytes, void *d_scratch, size_t scratch_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Segment reductions -- replace sec_mean / sec_min / sec_max (sec_mean/sec_mean.cu:13-93) and

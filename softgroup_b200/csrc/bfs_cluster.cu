@@ -28,7 +28,10 @@ struct BfsWs {
   unsigned long long *key;  // [N]
   int32_t *root_of;    // [N] cluster id -> seed
   int32_t *wins;       // [N] per queue position
-  int32_t *scalars;    // 0: changed flag, 1..: spare
+  int32_t *cid_of;     // [N] seed -> cluster id (kept) or -1
+  int32_t *members;    // [N] nodes of kept clusters, grouped by cluster (unordered inside)
+  int32_t *cursor;     // [N] per-cluster fill cursor / per-cluster level totals
+  int32_t *scalars;    // 0: changed flag, 1: max list length, 2..: spare
   long long *totals;   // [1] packed total
   long long *scan_tmp;
 };
@@ -44,6 +47,9 @@ static bool bfs_carve(void *ws, size_t bytes, int N, BfsWs &w) {
   w.key = a.take<unsigned long long>(n1);
   w.root_of = a.take<int32_t>(n1);
   w.wins = a.take<int32_t>(n1);
+  w.cid_of = a.take<int32_t>(n1);
+  w.members = a.take<int32_t>(n1);
+  w.cursor = a.take<int32_t>(n1);
   w.scan_tmp = a.take<long long>(scan_temp_elems(n1));
   return w.scan_tmp != nullptr;
 }
@@ -83,9 +89,12 @@ __global__ void bfs_propagate_kernel(const int32_t *__restrict__ idxs, const int
   if (__any_sync(0xffffffffu, changed) && lane == 0) w.scalars[0] = 1;
 }
 
-__global__ void bfs_size_kernel(int N, BfsWs w) {
+__global__ void bfs_size_kernel(int N, const int32_t *__restrict__ start_len, BfsWs w) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = v < N;
+  int len = active ? __ldg(&start_len[2 * (size_t)v + 1]) : 0;
+  len = __reduce_max_sync(0xffffffffu, len);
+  if ((threadIdx.x & 31) == 0 && len > *(volatile int32_t *)&w.scalars[1]) atomicMax(&w.scalars[1], len);
   int l = active ? w.label[v] : -1;
   unsigned am = __ballot_sync(0xffffffffu, active);
   if (!active) return;
@@ -111,6 +120,7 @@ __global__ void bfs_roots_kernel(int N, int nCluster, int sumNPoint, int32_t *__
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v == 0) cluster_offsets[nCluster] = sumNPoint;
   if (v >= N) return;
+  int cid = -1;
   if (w.label[v] == v) {
     long long p = w.packed[v];
     // a seed is kept iff the exclusive prefix grows by one cluster after it
@@ -119,8 +129,22 @@ __global__ void bfs_roots_kernel(int N, int nCluster, int sumNPoint, int32_t *__
       int c = (int)(p >> 32);
       w.root_of[c] = v;
       cluster_offsets[c] = (int)(p & 0xFFFFFFFFll);
+      cid = c;
     }
   }
+  w.cid_of[v] = cid;
+}
+
+// members of kept clusters grouped by cluster (order inside a group is irrelevant); key = "unvisited, label"
+__global__ void bfs_members_kernel(int N, const int32_t *__restrict__ cluster_offsets, BfsWs w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  int l = w.label[v];
+  w.key[v] = (0xFFFFFFFFull << 32) | (unsigned long long)(unsigned)l;
+  int c = w.cid_of[l];
+  if (c < 0) return;
+  int pos = atomicAdd(&w.cursor[c], 1);
+  w.members[cluster_offsets[c] + pos] = v;
 }
 
 constexpr int kEmitThreads = 256;
@@ -230,6 +254,154 @@ __global__ void __launch_bounds__(kEmitThreads) bfs_emit_kernel(const int32_t *_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// emit v2: one THREAD-BLOCK CLUSTER (8 CTAs, hardware barrier.cluster) per component, one pass over the edges
+// per BFS level.
+//   A  (edges of the frontier, all warps of the cluster): one 8-byte L2 read of key[v] per edge; key[v] holds
+//      either "unvisited | label" or the best (parent position, list slot) claim so far; claim with atomicMin
+//      only when it improves. Nodes of other components are told apart by the label half of the unvisited key.
+//   B' (members of the component, not edges): nodes claimed in this level set bit `slot` in their parent's bitmap
+//      row (rows are indexed by queue position; every position is a parent exactly once, so the bitmap is cleared
+//      once per call).
+//   counts = popcount per row -> exclusive scan over the frontier (CTA 0) -> C': every claimed node is written at
+//      b + offset(parent) + #set bits below its slot: queue order = (parent position, list slot), no sort.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCl = 8;          // CTAs per cluster (portable maximum)
+constexpr int kClThreads = 512;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
+    bfs_emit2_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len,
+                     const int32_t *__restrict__ cluster_offsets, int32_t *__restrict__ cluster_idxs, int nCluster, int W,
+                     uint32_t *__restrict__ bitmap, BfsWs w) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int crank = (int)cluster_ctarank();
+  const int cl_id = blockIdx.x / kCl, n_cl = gridDim.x / kCl;
+  const int gtid = crank * kClThreads + tid, gthreads = kCl * kClThreads;
+  const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+  __shared__ int s_warp[kClThreads / 32];
+  __shared__ int s_carry;
+
+  for (int c = cl_id; c < nCluster; c += n_cl) {
+    const int seed = w.root_of[c];
+    const int base = cluster_offsets[c];
+    const int size = cluster_offsets[c + 1] - base;
+    int32_t *order = cluster_idxs + 2 * (size_t)base;
+    int32_t *wins = w.wins + base;
+    const int32_t *members = w.members + base;
+    uint32_t *bm = bitmap + (size_t)base * W;
+    if (gtid == 0) {
+      w.key[seed] = 0ull;
+      order[0] = c;
+      order[1] = seed;
+    }
+    int a = 0, b = 1;
+    while (true) {
+      cluster_sync_all();
+      // ---- A: claim over the edges of frontier [a,b) ---------------------------------------------------
+      for (int p = a + gwarp; p < b; p += gwarps) {
+        const int u = __ldcg(&order[2 * (size_t)p + 1]);
+        const int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+        const unsigned long long hi = (unsigned long long)(p + 1) << 32;
+        for (int j0 = 0; j0 < l; j0 += 128) {
+          int v[4];
+          unsigned long long k[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            int j = j0 + t * 32 + lane;
+            v[t] = (j < l) ? __ldg(&idxs[(size_t)s + j]) : -1;
+          }
+#pragma unroll
+          for (int t = 0; t < 4; t++) k[t] = (v[t] >= 0) ? __ldcg(&w.key[v[t]]) : 0ull;
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            if (v[t] < 0) continue;
+            const unsigned long long mine = hi | (unsigned)(j0 + t * 32 + lane);
+            if (k[t] > mine && ((uint32_t)(k[t] >> 32) != 0xFFFFFFFFu || (uint32_t)k[t] == (uint32_t)seed))
+              atomicMin(&w.key[v[t]], mine);
+          }
+        }
+      }
+      cluster_sync_all();
+      // ---- B': members claimed in this level mark (parent row, slot) ------------------------------------
+      for (int m = gtid; m < size; m += gthreads) {
+        const int v = members[m];
+        const unsigned long long k = __ldcg(&w.key[v]);
+        const uint32_t pp = (uint32_t)(k >> 32);
+        if (pp >= (uint32_t)(a + 1) && pp <= (uint32_t)b) {
+          const uint32_t j = (uint32_t)k;
+          atomicOr(&bm[(size_t)(pp - 1) * W + (j >> 5)], 1u << (j & 31));
+        }
+      }
+      cluster_sync_all();
+      // ---- counts per parent ------------------------------------------------------------------------------
+      for (int p = a + gtid; p < b; p += gthreads) {
+        int cnt = 0;
+        for (int x = 0; x < W; x++) cnt += __popc(__ldcg(&bm[(size_t)p * W + x]));
+        wins[p] = cnt;
+      }
+      cluster_sync_all();
+      // ---- exclusive scan of wins[a..b) by CTA 0 ------------------------------------------------------------
+      if (crank == 0) {
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        const int warp = tid >> 5;
+        for (int p0 = a; p0 < b; p0 += kClThreads) {
+          int p = p0 + tid;
+          int x = (p < b) ? __ldcg(&wins[p]) : 0;
+          int inc = x;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (lane == 31) s_warp[warp] = inc;
+          __syncthreads();
+          int woff = 0;
+          for (int q = 0; q < warp; q++) woff += s_warp[q];
+          int carry = s_carry;
+          if (p < b) wins[p] = carry + woff + inc - x;
+          __syncthreads();
+          if (tid == kClThreads - 1) s_carry = carry + woff + inc;
+          __syncthreads();
+        }
+        if (tid == 0) w.cursor[c] = s_carry;  // level total (cursor[] is free again after bfs_members_kernel)
+      }
+      cluster_sync_all();
+      const int total = __ldcg(&w.cursor[c]);
+      if (total == 0) break;
+      // ---- C': place the claimed members --------------------------------------------------------------------
+      for (int m = gtid; m < size; m += gthreads) {
+        const int v = members[m];
+        const unsigned long long k = __ldcg(&w.key[v]);
+        const uint32_t pp = (uint32_t)(k >> 32);
+        if (pp >= (uint32_t)(a + 1) && pp <= (uint32_t)b) {
+          const uint32_t j = (uint32_t)k;
+          const uint32_t *row = bm + (size_t)(pp - 1) * W;
+          int rank = 0;
+          for (uint32_t x = 0; x < (j >> 5); x++) rank += __popc(__ldcg(&row[x]));
+          rank += __popc(__ldcg(&row[j >> 5]) & ((1u << (j & 31)) - 1u));
+          const int pos = b + __ldcg(&wins[pp - 1]) + rank;
+          order[2 * (size_t)pos] = c;
+          order[2 * (size_t)pos + 1] = v;
+        }
+      }
+      a = b;
+      b += total;
+    }
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
@@ -239,23 +411,25 @@ extern "C" {
 size_t sgb_bfs_cluster_workspace_bytes(int N) {
   if (N < 0) N = 0;
   size_t n1 = (size_t)N + 1;
-  size_t b = align_up(64 * 4) + align_up(64) + 4 * align_up(n1 * 4) + 2 * align_up(n1 * 8) +
+  size_t b = align_up(64 * 4) + align_up(64) + 7 * align_up(n1 * 4) + 2 * align_up(n1 * 8) +
              align_up(scan_temp_elems(n1) * 8);
   return b + 1024;
 }
 
 int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, float thr,
                           const int32_t *d_node_seg, const float *d_seg_thr, int symmetric_hint, void *d_ws,
-                          size_t ws_bytes, int *h_sumNPoint, void *stream) {
+                          size_t ws_bytes, int *h_sumNPoint, int *h_maxLen, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   (void)symmetric_hint;
   SGB_REQUIRE(N >= 0 && h_sumNPoint, SGB_ERR_ARG, "bfs_cluster arguments");
+  if (h_maxLen) *h_maxLen = 0;
   if (N == 0) { *h_sumNPoint = 0; return 0; }
   SGB_REQUIRE(d_start_len && d_ws, SGB_ERR_ARG, "null pointer");
   SGB_REQUIRE((d_node_seg == nullptr) == (d_seg_thr == nullptr), SGB_ERR_ARG, "node_seg / seg_thr must come together");
   BfsWs w;
   SGB_REQUIRE(bfs_carve(d_ws, ws_bytes, N, w), SGB_ERR_WORKSPACE, "bfs_cluster workspace too small");
   int nb = div_up(N, 256);
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 64 * 4, st));
   bfs_init_kernel<<<nb, 256, 0, st>>>(N, w);
   SGB_LAUNCH_CHECK();
   int grid = std::min(div_up((long long)N * 32, 256), kNumSMs * 16);
@@ -268,22 +442,31 @@ int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_sta
     SGB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (!changed) break;
   }
-  bfs_size_kernel<<<nb, 256, 0, st>>>(N, w);
+  bfs_size_kernel<<<nb, 256, 0, st>>>(N, d_start_len, w);
   SGB_LAUNCH_CHECK();
   bfs_pack_kernel<<<nb, 256, 0, st>>>(N, thr, d_node_seg, d_seg_thr, w);
   SGB_LAUNCH_CHECK();
   int rc = exclusive_scan_i64(w.packed, w.packed, (size_t)N, w.totals, w.scan_tmp, st);
   if (rc) return rc;
   long long tot = 0;
+  int sc[4];
   SGB_CUDA_CHECK(cudaMemcpyAsync(&tot, w.totals, 8, cudaMemcpyDeviceToHost, st));
+  SGB_CUDA_CHECK(cudaMemcpyAsync(sc, w.scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
   SGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_maxLen) *h_maxLen = sc[1];
   *h_sumNPoint = (int)(tot & 0xFFFFFFFFll);
   return (int)(tot >> 32);
 }
 
+size_t sgb_bfs_cluster_scratch_bytes(int sumNPoint, int maxLen) {
+  int W = (std::max(maxLen, 1) + 31) / 32;
+  if (W > 64) return 0;  // long-list fallback path needs no bitmap
+  return (size_t)std::max(sumNPoint, 1) * W * 4 + 256;
+}
+
 int sgb_bfs_cluster_fill(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, int nCluster,
-                         int sumNPoint, int32_t *d_cluster_idxs, int32_t *d_cluster_offsets, void *d_ws,
-                         size_t ws_bytes, void *stream) {
+                         int sumNPoint, int maxLen, int32_t *d_cluster_idxs, int32_t *d_cluster_offsets, void *d_ws,
+                         size_t ws_bytes, void *d_scratch, size_t scratch_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SGB_REQUIRE(N >= 0 && nCluster >= 0 && sumNPoint >= 0 && d_cluster_offsets, SGB_ERR_ARG, "bfs_cluster_fill arguments");
   if (N == 0 || nCluster == 0) {
@@ -293,12 +476,28 @@ int sgb_bfs_cluster_fill(const int32_t *d_ball_query_idxs, const int32_t *d_star
   SGB_REQUIRE(d_start_len && d_cluster_idxs && d_ws, SGB_ERR_ARG, "null pointer");
   BfsWs w;
   SGB_REQUIRE(bfs_carve(d_ws, ws_bytes, N, w), SGB_ERR_WORKSPACE, "bfs_cluster workspace too small");
-  bfs_roots_kernel<<<div_up(N, 256), 256, 0, st>>>(N, nCluster, sumNPoint, d_cluster_offsets, w);
+  int nb = div_up(N, 256);
+  bfs_roots_kernel<<<nb, 256, 0, st>>>(N, nCluster, sumNPoint, d_cluster_offsets, w);
   SGB_LAUNCH_CHECK();
-  SGB_CUDA_CHECK(cudaMemsetAsync(w.key, 0xFF, (size_t)N * 8, st));
-  bfs_emit_kernel<<<nCluster, kEmitThreads, 0, st>>>(d_ball_query_idxs, d_start_len, d_cluster_offsets,
-                                                     d_cluster_idxs, w);
-  SGB_LAUNCH_CHECK();
+  int W = (std::max(maxLen, 1) + 31) / 32;
+  if (W <= 64) {
+    size_t need = (size_t)sumNPoint * W * 4;
+    SGB_REQUIRE(d_scratch && scratch_bytes >= need, SGB_ERR_WORKSPACE, "bfs_cluster_fill scratch too small");
+    SGB_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, need, st));
+    SGB_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, (size_t)nCluster * 4, st));
+    bfs_members_kernel<<<nb, 256, 0, st>>>(N, d_cluster_offsets, w);
+    SGB_LAUNCH_CHECK();
+    int n_cl = std::min(nCluster, kNumSMs / kCl);
+    bfs_emit2_kernel<<<n_cl * kCl, kClThreads, 0, st>>>(d_ball_query_idxs, d_start_len, d_cluster_offsets, d_cluster_idxs,
+                                                       nCluster, W, (uint32_t *)d_scratch, w);
+    SGB_LAUNCH_CHECK();
+  } else {
+    // lists longer than 2048 entries (never produced by the ball queries): per-CTA rescan kernel
+    SGB_CUDA_CHECK(cudaMemsetAsync(w.key, 0xFF, (size_t)N * 8, st));
+    bfs_emit_kernel<<<nCluster, kEmitThreads, 0, st>>>(d_ball_query_idxs, d_start_len, d_cluster_offsets,
+                                                       d_cluster_idxs, w);
+    SGB_LAUNCH_CHECK();
+  }
   return SGB_OK;
 }
 }

@@ -32,8 +32,9 @@ SIGNATURES = {
     'sgb_ballquery_batch_p_async': (c_int, [c_int, c_longlong, c_float, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                             _P]),
     'sgb_bfs_cluster_workspace_bytes': (c_size_t, [c_int]),
-    'sgb_bfs_cluster_count': (c_int, [_P, _P, c_int, c_float, _P, _P, c_int, _P, c_size_t, _INTP, _P]),
-    'sgb_bfs_cluster_fill': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    'sgb_bfs_cluster_count': (c_int, [_P, _P, c_int, c_float, _P, _P, c_int, _P, c_size_t, _INTP, _INTP, _P]),
+    'sgb_bfs_cluster_scratch_bytes': (c_size_t, [c_int, c_int]),
+    'sgb_bfs_cluster_fill': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P, c_size_t, _P]),
     'sgb_sec_mean': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'sgb_sec_min': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'sgb_sec_max': (c_int, [_P, _P, _P, c_int, c_int, _P]),

@@ -102,18 +102,22 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     N = start_len.size(0)
     ws = _ws(L.sgb_bfs_cluster_workspace_bytes(N), dev)
     s = ctypes.c_int(0)
+    mx = ctypes.c_int(0)
     nact = ball_query_idxs.numel()
     with profiler.record('bfs_cluster(label)', 8 * N + 4 * nact):
         nC = check(
             L.sgb_bfs_cluster_count(ptr(ball_query_idxs), ptr(start_len), N, float(thr), ptr(node_seg), ptr(seg_thr),
-                                    int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), _stream()),
+                                    int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), ctypes.byref(mx),
+                                    _stream()),
             'sgb_bfs_cluster_count')
     cluster_idxs = torch.empty((s.value, 2), dtype=torch.int32, device=dev)
     cluster_offsets = torch.empty(nC + 1, dtype=torch.int32, device=dev)
+    scratch = _ws(L.sgb_bfs_cluster_scratch_bytes(s.value, mx.value), dev)
     with profiler.record('bfs_cluster(emit)', 8 * N + 4 * nact + 8 * s.value + 4 * (nC + 1)):
         check(
-            L.sgb_bfs_cluster_fill(ptr(ball_query_idxs), ptr(start_len), N, nC, s.value, ptr(cluster_idxs),
-                                   ptr(cluster_offsets), ptr(ws), ws.numel(), _stream()), 'sgb_bfs_cluster_fill')
+            L.sgb_bfs_cluster_fill(ptr(ball_query_idxs), ptr(start_len), N, nC, s.value, mx.value, ptr(cluster_idxs),
+                                   ptr(cluster_offsets), ptr(ws), ws.numel(), ptr(scratch), scratch.numel(),
+                                   _stream()), 'sgb_bfs_cluster_fill')
     return cluster_idxs, cluster_offsets
 
 
