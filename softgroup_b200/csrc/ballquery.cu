@@ -21,7 +21,7 @@ namespace sgb {
 
 constexpr int kBqThreads = 256;
 constexpr int kBqWarps = kBqThreads / 32;
-constexpr int kBqSMax = 4096;  // staged candidates per cell (16 B each)
+constexpr int kBqSMax = 8192;  // staged candidates per cell (16 B each, 128 KB)
 constexpr int kCellBias = 131072;
 constexpr int kMaxSeg = 1023;
 
@@ -200,16 +200,16 @@ __global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__res
       }
       for (int t = total_s + tid; t < P; t += kBqThreads) S[t] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
       __syncthreads();
+      // bitonic sort by point index; every thread owns compare-exchange pairs (no idle half)
       for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int t = tid; t < P; t += kBqThreads) {
-            int u = t ^ j;
-            if (u > t) {
-              float4 a = S[t], b = S[u];
-              bool asc = ((t & k) == 0);
-              bool gt = __float_as_int(a.w) > __float_as_int(b.w);
-              if (gt == asc) { S[t] = b; S[u] = a; }
-            }
+          for (int q = tid; q < (P >> 1); q += kBqThreads) {
+            const int t = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+            const int u = t | j;
+            float4 a = S[t], b = S[u];
+            const bool asc = ((t & k) == 0);
+            const bool gt = __float_as_int(a.w) > __float_as_int(b.w);
+            if (gt == asc) { S[t] = b; S[u] = a; }
           }
           __syncthreads();
         }

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import spconv
-from ..ops import (ballquery_batch_p, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
+from ..ops import (ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
                    voxelization_idx)
 from ..util import cuda_cast, force_fp32, rle_encode_ids
 from .blocks import MLP, ResidualBlock, UBlock
@@ -291,7 +291,7 @@ class SoftGroup(nn.Module):
         seg_offsets = torch.zeros(nseg + 1, dtype=torch.int32, device=dev)
         seg_offsets[1:] = seg_counts.cumsum(0).int()
         shifted = (coords_float[pts] + pt_offsets[pts]).contiguous()
-        neighbor_inds, start_len = ballquery_batch_p(shifted, seg, seg_offsets, radius, mean_active)
+        neighbor_inds, start_len, _ = ballquery_batch_p_nosync(shifted, seg, seg_offsets, radius)
         # per-segment thresholds: threshold*mean or absolute when mean == -1 (bfs_cluster.cpp:70-77), float32 math
         thr_c = torch.tensor([npoint_thr if cnm[c] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[c]))
                               for c in classes], dtype=torch.float32, device=dev)

@@ -90,6 +90,31 @@ class BallQueryBatchP(Function):
 ballquery_batch_p = BallQueryBatchP.apply
 
 
+def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
+    """Device-resident variant for the fused forward: the index buffer is sized for the cap (n * 1000 entries, only
+    the used prefix is ever touched), so there is no overflow relaunch (functions.py:258-266 of the reference) and
+    no host synchronisation. Returns (idx buffer int32 [n*1000], start_len int32 [n,2], total int32 [1] on device);
+    only idx[start:start+len] per point is meaningful."""
+    n = coords.size(0)
+    assert coords.is_contiguous() and coords.is_cuda
+    L = _lib.lib()
+    dev = coords.device
+    B = batch_offsets.numel() - 1
+    start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    cap = max(n, 1) * 1000
+    idx = torch.empty(cap, dtype=torch.int32, device=dev)
+    if n == 0:
+        return idx, start_len, total
+    ws = _ws(L.sgb_ballquery_workspace_bytes(n), dev)
+    with profiler.record('ballquery_batch_p', 24 * n + 4 * (B + 1)) as rec:
+        check(
+            L.sgb_ballquery_batch_p_async(n, cap, float(radius), ptr(coords), ptr(batch_idxs), ptr(batch_offsets), B,
+                                          ptr(idx), ptr(start_len), ptr(total), ptr(ws), ws.numel(), _stream()),
+            'sgb_ballquery_batch_p_async')
+    return idx, start_len, total
+
+
 # ----------------------------------------------------------------------------------------------
 # clustering
 # ----------------------------------------------------------------------------------------------
