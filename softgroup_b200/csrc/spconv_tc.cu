@@ -2,9 +2,9 @@
 //
 // One CTA owns a tile of 128 output rows x N = Cout columns. For every kernel offset with at least one active
 // pair in the tile and every 32-channel slice of Cin:
-//   * the 128 threads gather one input row slice each (eval-BatchNorm + ReLU folded in), split every value into
-//     a TF32-exact high part and an fp32 remainder, and store both as UMMA "K-major, no swizzle" core matrices
-//     (8 rows x 16 B, contiguous 128 B) in shared memory;
+//   * the producer threads gather one input row slice each (eval-BatchNorm + ReLU folded in), split every value into
+//     a TF32-exact high part and an fp32 remainder, and write both straight into TENSOR MEMORY with tcgen05.st
+//     (A operand from TMEM: lane = row, column = channel) -- the shared-memory pipe only carries the weights;
 //   * the pre-packed weight slice (same split, same core-matrix order, done once on the host side) is copied in;
 //   * one thread issues the three error-compensated products hi*hi + hi*lo + lo*hi as
 //     tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Cout, K=8 per instruction) accumulating fp32 in TMEM, then
@@ -34,7 +34,8 @@ struct TcArgs {
   const float *residual; int res_stride, res_off;
   const float *bias;
   float *out; int out_stride, out_off;
-  int nstages, nbstages, tmem_cols;  // A ring depth, B (weight) ring depth
+  int nstages, nbstages, tmem_cols, tmem_acols;  // A ring depth (TMEM), weight ring depth (smem), TMEM columns, first A column
+  long long *dbg;  // optional timeline buffer (test hook)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,6 +67,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+      "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+      "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor: core matrix = 8 rows x 16 B (128 contiguous bytes);
 // LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -93,7 +120,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // gathered row slice in registers while the current one is being split and stored, so the L2 latency of the gather
 // overlaps the stores, the weight copy (cp.async) and the other group's work. full[s]: 128 producer arrivals,
 // free[s]: tcgen05.commit, done: accumulator complete.
-__global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bars[20];  // [0..3] A full, [4..7] A free, [8] done, [10..14] B full, [15..19] B free
   __shared__ uint32_t s_tmem;
@@ -114,12 +141,10 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
   const int N = p.N, NT = p.NT;
   const int n0 = blockIdx.y * NT;
   const int nt = min(NT, N - n0);                     // columns of this CTA (multiple of 16)
-  const uint32_t a_bytes = TC_ROWS * TC_KC * 4;       // 16 KB
   const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;  // NT * 128 B
-  const uint32_t stage_bytes = 2 * a_bytes;     // A ring stage: hi + lo
-  const uint32_t bstage_bytes = 2 * b_bytes;    // B ring stage: hi + lo
-  const int NS = p.nstages, NSB = p.nbstages;
-  unsigned char *bring = smem + (size_t)NS * stage_bytes;
+  const uint32_t bstage_bytes = 2 * b_bytes;    // weight ring stage: hi + lo
+  const int NS = p.nstages, NSB = p.nbstages;   // NS: A stages in TMEM (64 columns each), NSB: weight stages in smem
+  unsigned char *bring = smem;
   int32_t *map_s = reinterpret_cast<int32_t *>(bring + (size_t)NSB * bstage_bytes);  // [K][128] (only when p.map)
 
   if (tid == 0) {
@@ -213,17 +238,20 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
     int s = grp % NS, u = grp / NS;
     if (i < total) load_iter(a_idx, kc);
     for (; i < total; i += 2) {
+      const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && r == 0 && i < 64;
+      if (dbg_on) p.dbg[i * 8 + 0] = clock64();
       if (u >= 1) mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((u - 1) & 1));
-      unsigned char *st = smem + (size_t)s * stage_bytes;
-      float4 *Ahi = reinterpret_cast<float4 *>(st);
-      float4 *Alo = reinterpret_cast<float4 *>(st + a_bytes);
+      if (dbg_on) p.dbg[i * 8 + 1] = clock64();
       const int c0 = kc * TC_KC;
       const int kvalid = min(TC_KC, p.Cin - c0);
-      const int ksteps = (kvalid + 7) >> 3;
-      // ---- A: registers -> (BN+ReLU) -> hi / lo core matrices ---------------------------------------------
+      // ---- A: registers -> (BN+ReLU) -> hi / lo -> tensor memory (lane = row, column = channel) -----------
+      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 64);
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        if (q < 2 * ksteps) {
+      for (int hq = 0; hq < 2; hq++) {  // 16 channels at a time keeps the register footprint at two CTAs per SM
+        uint32_t hv[16], lv[16];
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++) {
+          const int q = hq * 4 + qq;
           float4 x = v[q];
           if (has_act && vsrc >= 0) {
             const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[c0 + 4 * q]);
@@ -239,19 +267,25 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
               if (4 * q + 3 >= kvalid) x.w = 0.f;
             }
           }
-          float4 h = tf32_hi(x);
-          float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-          Ahi[q * TC_ROWS + r] = h;  // chunk q, row r: byte offset q*2048 + r*16
-          Alo[q * TC_ROWS + r] = l;
+          const float4 h = tf32_hi(x);
+          hv[4 * qq + 0] = __float_as_uint(h.x); hv[4 * qq + 1] = __float_as_uint(h.y);
+          hv[4 * qq + 2] = __float_as_uint(h.z); hv[4 * qq + 3] = __float_as_uint(h.w);
+          lv[4 * qq + 0] = __float_as_uint(x.x - h.x); lv[4 * qq + 1] = __float_as_uint(x.y - h.y);
+          lv[4 * qq + 2] = __float_as_uint(x.z - h.z); lv[4 * qq + 3] = __float_as_uint(x.w - h.w);
         }
+        tmem_st16(ta + (uint32_t)(hq * 16), hv);
+        tmem_st16(ta + 32u + (uint32_t)(hq * 16), lv);
       }
       const int s_done = s;
       kc += 2;
       while (kc >= nkc) { kc -= nkc; a_idx++; }
       s += 2;
       if (s >= NS) { s -= NS; u++; }
+      if (dbg_on) p.dbg[i * 8 + 2] = clock64();
       if (i + 2 < total) load_iter(a_idx, kc);  // next gather of this group is in flight during the waits below
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (dbg_on) p.dbg[i * 8 + 3] = clock64();
       mbar_arrive(smem_u32(&bars[s_done]));
     }
   } else if (warp == 9) {
@@ -259,7 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
     //      no generic->async fence needed) into a deeper ring; completion is signalled on the stage's mbarrier by
     //      complete_tx. Global layout [chunk q][hi|lo][N][16 B] == shared layout [q][hi nt | lo nt][16 B] when the CTA
     //      owns all N columns, so a whole slice is ONE bulk copy; with a column split it is one copy per (q, part).
-    if (lane == 0) {
+    {
       int sb = 0, ub = 0, kc = 0, a_idx = 0;
       for (int i = 0; i < total; i++) {
         if (ub >= 1) mbar_wait(smem_u32(&bars[15 + sb]), (uint32_t)((ub - 1) & 1));
@@ -271,16 +305,17 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
         const uint32_t bar = smem_u32(&bars[10 + sb]);
         const int nseg = 4 * ksteps;  // (chunk, part) segments of nt*16 bytes
         const uint32_t bytes = (uint32_t)nseg * (uint32_t)nt * 16u;
-        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+        if (lane == 0)
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+        __syncwarp();
         if (nt == N) {
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(bb), "l"(g), "r"(bytes), "r"(bar) : "memory");
-        } else {
-          for (int j = 0; j < nseg; j++) {
+          if (lane == 0)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(bb + (uint32_t)(j * nt) * 16u), "l"(g + (size_t)j * N + n0), "r"((uint32_t)nt * 16u), "r"(bar)
-                         : "memory");
-          }
+                         ::"r"(bb), "l"(g), "r"(bytes), "r"(bar) : "memory");
+        } else if (lane < nseg) {  // column split: one bulk copy per (chunk, part) segment, one lane each
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(bb + (uint32_t)(lane * nt) * 16u), "l"(g + (size_t)lane * N + n0), "r"((uint32_t)nt * 16u), "r"(bar)
+                       : "memory");
         }
         if (++sb == NSB) { sb = 0; ub++; }
         if (++kc == nkc) { kc = 0; a_idx++; }
@@ -295,39 +330,42 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
     //      a single thread's instruction stream paces the tensor pipe (measured ~50 cycles / tcgen05.mma at N<=64).
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * nt) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
     const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-    const uint32_t a_lbo = TC_ROWS * 16, b_lbo = (uint32_t)(2 * nt) * 16;
-    const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), b_step = (uint64_t)((2 * b_lbo) >> 4);
+    const uint32_t b_lbo = (uint32_t)(2 * nt) * 16;
+    const uint64_t b_step = (uint64_t)((2 * b_lbo) >> 4);
     uint32_t first = 0u;  // 0 for the very first MMA (overwrite), then 1
     int s = 0, sb = 0, kc = 0;
     uint32_t pa = 0u, pb = 0u;
     for (int i = 0; i < total; i++) {
+      const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && i < 64;
+      if (dbg_on) p.dbg[i * 8 + 4] = clock64();
       mbar_wait(smem_u32(&bars[10 + sb]), pb);
+      if (dbg_on) p.dbg[i * 8 + 5] = clock64();
       mbar_wait(smem_u32(&bars[s]), pa);
+      if (dbg_on) p.dbg[i * 8 + 6] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
       const int ksteps = (kvalid + 7) >> 3;
-      const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t sbt = smem_u32(bring + (size_t)sb * bstage_bytes);
-      uint64_t dah = umma_desc(st, a_lbo, 128);
-      uint64_t dal = umma_desc(st + a_bytes, a_lbo, 128);
       uint64_t dbb = umma_desc(sbt, b_lbo, 128);
+      uint32_t ah = tmem + (uint32_t)(p.tmem_acols + s * 64), al = ah + 32u;
       if (ksteps == 4) {
 #pragma unroll
         for (int ks = 0; ks < 4; ks++) {
-          umma_tf32(tmem, dah, dbb, idesc2, (ks == 0) ? first : 1u);
-          umma_tf32(tmem + (uint32_t)nt, dal, dbb, idesc1, 1u);
-          dah += a_step; dal += a_step; dbb += b_step;
+          umma_tf32_ts(tmem, ah, dbb, idesc2, (ks == 0) ? first : 1u);
+          umma_tf32_ts(tmem + (uint32_t)nt, al, dbb, idesc1, 1u);
+          ah += 8u; al += 8u; dbb += b_step;
         }
       } else {
         for (int ks = 0; ks < ksteps; ks++) {
-          umma_tf32(tmem, dah, dbb, idesc2, (ks == 0) ? first : 1u);
-          umma_tf32(tmem + (uint32_t)nt, dal, dbb, idesc1, 1u);
-          dah += a_step; dal += a_step; dbb += b_step;
+          umma_tf32_ts(tmem, ah, dbb, idesc2, (ks == 0) ? first : 1u);
+          umma_tf32_ts(tmem + (uint32_t)nt, al, dbb, idesc1, 1u);
+          ah += 8u; al += 8u; dbb += b_step;
         }
       }
       first = 1u;
       umma_commit(smem_u32(&bars[4 + s]));    // frees the A stage once the MMAs above have read it
       umma_commit(smem_u32(&bars[15 + sb]));  // ... and the weight stage
+      if (dbg_on) p.dbg[i * 8 + 7] = clock64();
       if (++s == NS) { s = 0; pa ^= 1u; }
       if (++sb == NSB) { sb = 0; pb ^= 1u; }
       if (++kc == nkc) kc = 0;
@@ -387,7 +425,11 @@ __global__ void __launch_bounds__(TC_THREADS) spconv_tc_kernel(TcArgs p) {
 
 using namespace sgb;
 
+static long long *g_tc_dbg = nullptr;
+
 extern "C" {
+
+void sgb_test_set_tc_debug(long long *d_buf) { g_tc_dbg = d_buf; }
 
 // Packed weight size in floats for sgb_spconv_forward_tc: K * ceil(Cin/32) * 8 * N * 4 with N = Cout rounded to 16.
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout) {
@@ -416,6 +458,7 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   p.residual = d_residual; p.res_stride = res_stride; p.res_off = res_off;
   p.bias = d_bias;
   p.out = d_out; p.out_stride = out_stride; p.out_off = out_off;
+  p.dbg = g_tc_dbg;
   // Column split: few row tiles (deep U-Net levels) would leave most SMs idle and make one CTA stream all the
   // weights, so N is cut into NT-column CTAs until the grid covers the machine (NT multiple of 16, >= 32).
   int tiles = div_up(Mout, TC_ROWS);
@@ -427,25 +470,22 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
     NT = nxt;
   }
   p.NT = NT;
-  size_t stage = 2 * (size_t)TC_ROWS * TC_KC * 4;  // A ring stage (hi + lo)
-  size_t bstage = 2 * (size_t)NT * TC_KC * 4;      // weight ring stage (hi + lo)
+  size_t bstage = 2 * (size_t)NT * TC_KC * 4;      // weight ring stage (hi + lo) in shared memory
   size_t map_bytes = d_map ? (size_t)K * TC_ROWS * 4 : 0;
-  // two CTAs per SM (2 A stages + 4 weight stages) when that fits, else one CTA with deeper rings
-  p.nstages = 2;
-  p.nbstages = 4;
-  if (2 * (p.nstages * stage + p.nbstages * bstage + map_bytes + 2048) > 225 * 1024) {
-    p.nstages = 3;
-    size_t left = 210 * 1024 - map_bytes - p.nstages * stage;
-    p.nbstages = (int)std::max<size_t>(2, std::min<size_t>(4, left / bstage));
-    if (p.nbstages * bstage + p.nstages * stage + map_bytes > 210 * 1024) p.nstages = 2;
-  }
-  int cols = 32;
-  while (cols < 2 * NT) cols <<= 1;
-  p.tmem_cols = cols;
-  size_t smem = stage * p.nstages + bstage * p.nbstages + map_bytes + 1024;
+  // TMEM budget: accumulator [main | corrections] = 2*NT columns, then the A ring (64 columns per stage: hi + lo).
+  // 256 columns (two CTAs per SM) when that leaves >= 2 A stages, else all 512.
+  int dcols = 2 * NT;
+  int acols0 = (dcols + 31) / 32 * 32;
+  if (acols0 + 2 * 64 <= 256) { p.tmem_cols = 256; p.nstages = (256 - acols0) / 64; }
+  else { p.tmem_cols = 512; p.nstages = (512 - acols0) / 64; }
+  p.nstages = std::min(p.nstages, 4);
+  p.tmem_acols = acols0;
+  p.nbstages = (int)std::max<size_t>(2, std::min<size_t>(4, (96 * 1024 - map_bytes) / bstage));
+  size_t smem = bstage * p.nbstages + map_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid(tiles, div_up(N, NT));
@@ -457,15 +497,6 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
 
 // ---- micro-benchmark hook: cost of back-to-back tcgen05.mma kind::tf32 (M=128, N, K=8) into one accumulator ----
 namespace sgb {
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __global__ void umma_rate_kernel(int N, int reps, int per_commit, long long *out, int a_in_tmem) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;

@@ -185,7 +185,7 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    use_tc = CONV_IMPL == 'tc' and Cout <= 256 and Cin <= 256
+    use_tc = CONV_IMPL == 'tc' and Cout <= 256 and Cin <= 512
     name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
     with profiler.record(name, nbytes):
         if use_tc:
