@@ -49,10 +49,10 @@ def rle_encode_many(ids, offs, length):
     cap = int(ids.size) * 24 + 64 * n + 64
     out = np.empty(cap, dtype=np.uint8)
     out_offs = np.empty(n + 1, dtype=np.int64)
-    _lib.check(
+    written = _lib.check(
         _lib.lib().sgb_rle_format_ids(ids.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p), n,
                                       out.ctypes.data_as(ctypes.c_void_p), cap,
                                       out_offs.ctypes.data_as(ctypes.c_void_p)), 'sgb_rle_format_ids')
-    buf = out.tobytes()
+    buf = out[:written].tobytes()
     o = out_offs.tolist()
     return [dict(length=length, counts=buf[o[k]:o[k + 1]].decode('ascii')) for k in range(n)]
