@@ -291,14 +291,14 @@ class SoftGroup(nn.Module):
         seg_offsets = torch.zeros(nseg + 1, dtype=torch.int32, device=dev)
         seg_offsets[1:] = seg_counts.cumsum(0).int()
         shifted = (coords_float[pts] + pt_offsets[pts]).contiguous()
-        neighbor_inds, start_len, _ = ballquery_batch_p_nosync(shifted, seg, seg_offsets, radius)
+        neighbor_inds, start_len, n_active = ballquery_batch_p_nosync(shifted, seg, seg_offsets, radius)
         # per-segment thresholds: threshold*mean or absolute when mean == -1 (bfs_cluster.cpp:70-77), float32 math
         thr_c = torch.tensor([npoint_thr if cnm[c] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[c]))
                               for c in classes], dtype=torch.float32, device=dev)
         seg_thr = thr_c.repeat_interleave(batch_size).contiguous()
         capped = False  # lists that hit the 1000 cap make the graph asymmetric -> exact directed labelling
         cidx, coff = bfs_cluster_segments(neighbor_inds, start_len, 0.0, node_seg=seg, seg_thr=seg_thr,
-                                          symmetric=not capped)
+                                          symmetric=not capped, nactive=n_active)
         if cidx.size(0) == 0:
             return empty
         # proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1]] (:464)

@@ -107,7 +107,8 @@ def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
     if n == 0:
         return idx, start_len, total
     ws = _ws(L.sgb_ballquery_workspace_bytes(n), dev)
-    with profiler.record('ballquery_batch_p', 24 * n + 4 * (B + 1)) as rec:
+    # algorithmic bytes need nActive, which stays on the device: resolved lazily when the profiler is summarised
+    with profiler.record('ballquery_batch_p', lambda: 24 * n + 4 * (B + 1) + 4 * int(total.item())):
         check(
             L.sgb_ballquery_batch_p_async(n, cap, float(radius), ptr(coords), ptr(batch_idxs), ptr(batch_offsets), B,
                                           ptr(idx), ptr(start_len), ptr(total), ptr(ws), ws.numel(), _stream()),
@@ -118,7 +119,8 @@ def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
 # ----------------------------------------------------------------------------------------------
 # clustering
 # ----------------------------------------------------------------------------------------------
-def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, symmetric=False):
+def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, symmetric=False,
+                         nactive=None):
     """GPU clustering on device tensors. thr: float threshold on the component size (already multiplied by the
     class mean when that applies). Optional per-node segment thresholds. Returns CUDA tensors
     (cluster_idxs int32 [sumNPoint,2], cluster_offsets int32 [nCluster+1])."""
@@ -128,8 +130,9 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     ws = _ws(L.sgb_bfs_cluster_workspace_bytes(N), dev)
     s = ctypes.c_int(0)
     mx = ctypes.c_int(0)
-    nact = ball_query_idxs.numel()
-    with profiler.record('bfs_cluster(label)', 8 * N + 4 * nact):
+    nact = ball_query_idxs.numel() if nactive is None else nactive
+    nb = (lambda: int(nact.item())) if torch.is_tensor(nact) else (lambda: int(nact))
+    with profiler.record('bfs_cluster(label)', lambda: 8 * N + 4 * nb()):
         nC = check(
             L.sgb_bfs_cluster_count(ptr(ball_query_idxs), ptr(start_len), N, float(thr), ptr(node_seg), ptr(seg_thr),
                                     int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), ctypes.byref(mx),
@@ -138,7 +141,7 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     cluster_idxs = torch.empty((s.value, 2), dtype=torch.int32, device=dev)
     cluster_offsets = torch.empty(nC + 1, dtype=torch.int32, device=dev)
     scratch = _ws(L.sgb_bfs_cluster_scratch_bytes(s.value, mx.value), dev)
-    with profiler.record('bfs_cluster(emit)', 8 * N + 4 * nact + 8 * s.value + 4 * (nC + 1)):
+    with profiler.record('bfs_cluster(emit)', lambda: 8 * N + 4 * nb() + 8 * s.value + 4 * (nC + 1)):
         check(
             L.sgb_bfs_cluster_fill(ptr(ball_query_idxs), ptr(start_len), N, nC, s.value, mx.value, ptr(cluster_idxs),
                                    ptr(cluster_offsets), ptr(ws), ws.numel(), ptr(scratch), scratch.numel(),

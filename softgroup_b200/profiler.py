@@ -43,7 +43,7 @@ class record(object):
     def __exit__(self, *a):
         if _enabled:
             self.e1.record()
-            _records.append((self.name, float(self.nbytes), self.e0, self.e1))
+            _records.append((self.name, self.nbytes, self.e0, self.e1))
 
 
 def summary():
@@ -53,7 +53,7 @@ def summary():
     for name, nbytes, e0, e1 in _records:
         a = agg.setdefault(name, [0.0, 0.0, 0])
         a[0] += e0.elapsed_time(e1)
-        a[1] += nbytes
+        a[1] += float(nbytes() if callable(nbytes) else nbytes)
         a[2] += 1
     total_ms = sum(a[0] for a in agg.values()) or 1e-9
     by = {}

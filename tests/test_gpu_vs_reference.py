@@ -1,0 +1,138 @@
+"""GPU box only: this repo's kernels AND the oracle's restatements of the CUDA-only reference ops against the
+reference's OWN CUDA kernels, compiled unmodified into oracle/_ref (oracle/build_ref.py). Skipped when the
+prebuilt reference extension is not present."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from softgroup_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ref(ref_ops):
+    if ref_ops is None:
+        pytest.skip('oracle/_ref not built')
+    return ref_ops
+
+
+def _c(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _lists(idx, sl):
+    idx, sl = idx.cpu().numpy(), sl.cpu().numpy()
+    return [idx[s:s + l] for s, l in sl]
+
+
+def _ref_ballquery(ref, xyz, bi, bo, r, mean_active):
+    n = xyz.size(0)
+    while True:
+        idx = torch.zeros(n * mean_active, dtype=torch.int32, device='cuda')
+        sl = torch.zeros((n, 2), dtype=torch.int32, device='cuda')
+        na = ref.ballquery_batch_p(xyz, bi, bo, idx, sl, n, mean_active, r)
+        if na <= n * mean_active:
+            return idx[:na], sl
+        mean_active = int(na // n + 1)
+
+
+@pytest.mark.parametrize('n,sigma,r', [(3000, 0.03, 0.04), (2500, 0.006, 0.04), (4000, 0.2, 0.02)])
+def test_ballquery_vs_reference_kernel(ref, n, sigma, r):
+    rng = np.random.RandomState(n)
+    centers = rng.rand(6, 3)
+    xyz = (centers[rng.randint(0, 6, n)] + rng.randn(n, 3) * sigma).astype(np.float32)
+    cut = n // 3
+    bo = np.array([0, cut, n], np.int32)
+    bi = np.repeat(np.arange(2), np.diff(bo)).astype(np.int32)
+    ridx, rsl = _ref_ballquery(ref, _c(xyz), _c(bi), _c(bo), r, 100)
+    gidx, gsl = ops.ballquery_batch_p(_c(xyz), _c(bi), _c(bo), r, 100)
+    oidx, osl = oracle.ballquery_batch_p(xyz, bi, bo, r)
+    R, G = _lists(ridx, rsl), _lists(gidx, gsl)
+    O = [oidx[s:s + l] for s, l in osl]
+    for i in range(n):
+        assert np.array_equal(R[i], G[i]), i   # ours == reference kernel
+        assert np.array_equal(R[i], O[i]), i   # oracle restatement == reference kernel (pins the oracle)
+
+
+def test_voxelize_fp_vs_reference_kernel(ref):
+    rng = np.random.RandomState(1)
+    coords = np.concatenate([np.zeros((20000, 1), np.int64), rng.randint(0, 30, (20000, 3))], 1)
+    _, _, om = oracle.voxelization_idx(coords, 1, 4)
+    feats = rng.randn(20000, 32).astype(np.float32)
+    M = om.shape[0]
+    out = torch.zeros((M, 32), device='cuda')
+    ref.voxelize_fp(_c(feats), out, _c(om), 4, M, om.shape[1] - 1, 32)
+    ours = ops.voxelization(_c(feats), _c(om), 4)
+    assert np.array_equal(out.cpu().numpy(), ours.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), oracle.voxelization(feats, om, 4))
+
+
+def test_segment_ops_vs_reference_kernels(ref):
+    rng = np.random.RandomState(2)
+    lens = rng.randint(1, 700, 40)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    x = rng.randn(off[-1], 32).astype(np.float32)
+    xc, oc = _c(x), _c(off)
+    for name in ('sec_min', 'sec_max', 'sec_mean'):
+        out = torch.zeros((40, 32), device='cuda')
+        getattr(ref, name)(xc, oc, out, 40, 32)
+        want = out.cpu().numpy()
+        assert np.array_equal(want, getattr(oracle, name)(x, off)), name  # oracle == reference kernel
+        got = getattr(ops, name)(xc, oc).cpu().numpy()
+        if name == 'sec_mean':
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+        else:
+            assert np.array_equal(got, want)
+    out = torch.zeros((40, 32), device='cuda')
+    ref.global_avg_pool_fp(xc, oc, out, 40, 32)
+    assert np.array_equal(out.cpu().numpy(), oracle.global_avg_pool(x, off))
+    np.testing.assert_allclose(ops.global_avg_pool(xc, oc).cpu().numpy(), out.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_mask_ops_vs_reference_kernels(ref):
+    rng = np.random.RandomState(3)
+    N, nI, nP = 4000, 17, 25
+    labels = rng.randint(-1, nI, N).astype(np.int64)
+    labels[labels < 0] = -100
+    pointnum = np.bincount(labels[labels >= 0], minlength=nI).astype(np.int32)
+    cls = rng.randint(0, 18, nI).astype(np.int64)
+    cls[3] = -100
+    lens = rng.randint(1, 300, nP)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    pidx = rng.randint(0, N, off[-1]).astype(np.int32)
+    sig = rng.rand(off[-1]).astype(np.float32)
+    iou = torch.zeros((nP, nI), device='cuda')
+    ref.get_mask_iou_on_cluster(_c(pidx), _c(off), _c(labels), _c(pointnum), iou, nI, nP)
+    ours = ops.get_mask_iou_on_cluster(_c(pidx), _c(off), _c(labels), _c(pointnum))
+    assert np.array_equal(iou.cpu().numpy(), ours.cpu().numpy())
+    assert np.array_equal(iou.cpu().numpy(), oracle.get_mask_iou_on_cluster(pidx, off, labels, pointnum))
+    iou2 = torch.zeros((nP, nI), device='cuda')
+    ref.get_mask_iou_on_pred(_c(pidx), _c(off), _c(labels), _c(pointnum), iou2, nI, nP, _c(sig))
+    assert np.array_equal(iou2.cpu().numpy(),
+                          ops.get_mask_iou_on_pred(_c(pidx), _c(off), _c(labels), _c(pointnum), _c(sig)).cpu().numpy())
+    ml = torch.full((off[-1], ), -1.0, device='cuda')
+    ref.get_mask_label(_c(pidx), _c(off), _c(labels), _c(cls), iou, nI, nP, 0.02, ml)
+    ours = ops.get_mask_label(_c(pidx), _c(off), _c(labels), _c(cls), _c(pointnum), iou, 0.02)
+    assert np.array_equal(ml.cpu().numpy(), ours.cpu().numpy())
+
+
+def test_octree_oracle_vs_reference_kernel(ref):
+    """Pins the oracle's octree ball query (leaf-major order, box/sphere test contraction) on the reference kernel."""
+    rng = np.random.RandomState(4)
+    pts = (rng.rand(3000, 3) * np.array([3., 2., 1.])).astype(np.float32)
+    boxes, pt_inds, psl = oracle.build_octree(pts)
+    n = 3000
+    mean_active = 50
+    while True:
+        out_inds = torch.zeros(n * mean_active, dtype=torch.int32, device='cuda')
+        out_sl = torch.zeros((n, 2), dtype=torch.int32, device='cuda')
+        tot = ref.octree_ball_query(_c(pts), _c(boxes), _c(pt_inds), _c(psl), out_inds, out_sl, mean_active, 0.15)
+        if tot <= n * mean_active:
+            break
+        mean_active = int(tot // n + 1)
+    R = _lists(out_inds[:tot], out_sl)
+    oidx, osl = oracle.octree_ball_query(pts, 50, 0.15)
+    for i in range(n):
+        assert np.array_equal(R[i], oidx[osl[i, 0]:osl[i, 0] + osl[i, 1]]), i
