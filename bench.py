@@ -145,6 +145,8 @@ def cpu_path_once(scan, sd, cfg, use_ref):
 
     sem = mlp(pf, 'semantic_linear')
     off = mlp(pf, 'offset_linear')
+    if 'inj_scores' in scan:  # same synthetic point-wise predictions as the GPU arm (computed heads are discarded)
+        sem, off = scan['inj_scores'], scan['inj_offsets']
     e = np.exp(sem - sem.max(1, keepdims=True))
     prob = e / e.sum(1, keepdims=True)
     g = cfg['grouping_cfg']
@@ -191,6 +193,9 @@ def cpu_leg(args, sd, cfg, scan, steps, warmup):
         ref = None
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
+    from softgroup_b200 import synth as _synth
+    scan = dict(scan)
+    scan['inj_scores'], scan['inj_offsets'] = _synth.grouping_inputs(scan, sigma=0.03, seed=args.seed)
     sub = crop_scan(scan, args.cpu_sample_points)
     frac = sub['coords'].shape[0] / float(scan['coords'].shape[0])
     times, stages = [], None
@@ -332,8 +337,15 @@ def main():
         peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
         prof = profiler.summary()
         dom = prof['dominant']
+        traffic = None
+        try:  # dram__bytes_read+write of the dominant kernel from the committed ncu capture (per step, like achieved)
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel_traffic.json')))
+            if tj.get('kernel') == dom['name']:
+                traffic = tj['dram_bytes_per_step']
+        except Exception:
+            pass
         roofline = dict(bound='hbm', kernel=dom['name'], achieved=dom['gbs'], peak=hbm_peak, unit='GB/s',
-                        frac=dom['gbs'] / hbm_peak, traffic=None, peak_source=peak_src,
+                        frac=dom['gbs'] / hbm_peak, traffic=traffic, peak_source=peak_src,
                         launches_per_step=dom['launches_per_step'], avg_launch_us=dom['avg_us'],
                         share_of_step=dom['share'], algorithmic_bytes_per_step=dom['bytes_per_step'],
                         by_kernel=prof['by_kernel'])
