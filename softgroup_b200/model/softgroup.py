@@ -153,9 +153,13 @@ class SoftGroup(nn.Module):
             semantic_scores, pt_offsets = inject
         if x4_split:
             coords_float = self.merge_4_parts(coords_float)
-            semantic_labels = self.merge_4_parts(semantic_labels)
-            instance_labels = self.merge_4_parts(instance_labels)
-            pt_offset_labels = self.merge_4_parts(pt_offset_labels)
+            color_feats = color_feats  # the reference returns color_feats un-merged as well (softgroup.py:312-316)
+            if semantic_labels is not None:
+                semantic_labels = self.merge_4_parts(semantic_labels)
+            if instance_labels is not None:
+                instance_labels = self.merge_4_parts(instance_labels)
+            if pt_offset_labels is not None:
+                pt_offset_labels = self.merge_4_parts(pt_offset_labels)
         semantic_preds = semantic_scores.max(1)[1]
         ret = dict(scan_id=scan_ids[0] if scan_ids else None)
         if not device_only:

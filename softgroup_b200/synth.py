@@ -161,3 +161,26 @@ def grouping_inputs(scan, sigma=0.03, seed=0, logit=8.0):
     off = scan['pt_offset_labels'] + (rng.randn(n, 3) * sigma).astype(np.float32)
     off[scan['instance_labels'] < 0] = 0
     return scores, off.astype(np.float32)
+
+
+def to_x4_split(scan):
+    """S3DIS test-time layout (softgroup/data/s3dis.py:46-115): the cloud is cut into 4 interleaved pieces
+    (inds[k::4]) that go through the backbone one after another; per-point arrays are stored piece after piece,
+    coords carry the piece id in column 0 (each piece shifted to its own origin), batch_idxs stay 0, batch_size 4."""
+    n = scan['coords'].shape[0]
+    pieces = [np.arange(n)[k::4] for k in range(4)]
+    order = np.concatenate(pieces)
+    out = dict(scan)
+    for k in ('coords_float', 'feats', 'semantic_labels', 'instance_labels', 'pt_offset_labels'):
+        out[k] = scan[k][order]
+    coords = []
+    for b, piece in enumerate(pieces):
+        xyz = scan['coords_float'][piece].astype(np.float64) * scan['scale']
+        xyz -= xyz.min(0)
+        coords.append(np.concatenate([np.full((len(piece), 1), b, np.int64), xyz.astype(np.int64)], 1))
+    out['coords'] = np.concatenate(coords, 0)
+    out['batch_idxs'] = np.zeros(n, np.int32)
+    out['spatial_shape'] = np.clip(out['coords'][:, 1:].max(0) + 1, 128, None)
+    out['batch_size'] = 4
+    out['x4_order'] = order
+    return out

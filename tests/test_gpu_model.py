@@ -132,3 +132,84 @@ def test_end_to_end_result_dict():
         assert abs(float(a['conf']) - float(b['conf'])) < 1e-6
     m = rle_decode(ret['pred_instances'][0]['pred_mask'])
     assert m.shape == (30000, ) and m.sum() >= 100
+
+
+def test_x4_split_backbone_vs_oracle():
+    """S3DIS path (softgroup.py:380-409): 4 interleaved pieces through the backbone, merged back to point order."""
+    from oracle import spconv_oracle as so
+    scan = synth.to_x4_split(synth.make_scan('c3_s3dis', seed=1, n_points=12000))
+    torch.manual_seed(0)
+    model = SoftGroup(**model_cfg('s3dis', channels=16, num_blocks=4)).cuda().eval()
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    coords = scan['coords']
+    vc, v2p, p2v = oracle.voxelization_idx(coords, 4, 4)
+    feats = np.concatenate([scan['feats'], scan['coords_float']], 1).astype(np.float32)
+    vfeats = oracle.voxelization(feats, p2v, 4)
+    outs = []
+    for b in range(4):
+        sel = vc[:, 0] == b
+        idx = vc[sel].astype(np.int32).copy()
+        idx[:, 0] = 0
+        outs.append(so.backbone(vfeats[sel], idx, scan['spatial_shape'], sd, 16, 4, acc64=True))
+    want_piece_order = np.concatenate(outs, 0)[v2p]
+    n = coords.shape[0]
+    want = np.zeros_like(want_piece_order)
+    want[scan['x4_order']] = want_piece_order  # merge_4_parts: x_new[inds[k::4]] = piece k
+    with torch.no_grad():
+        from softgroup_b200 import spconv
+        x = spconv.SparseConvTensor(torch.from_numpy(vfeats).cuda(), torch.from_numpy(vc.astype(np.int32)).cuda(),
+                                    scan['spatial_shape'], 4)
+        got = model.forward_4_parts(x, torch.from_numpy(v2p).cuda())
+        got = model.merge_4_parts(got).cpu().numpy()
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
+
+
+def test_kitti_panoptic_end_to_end():
+    """KITTI config (softgroup_kitti.yaml): 1 input channel, no coords, panoptic fusion of the instances."""
+    scan = synth.make_scan('c4_kitti', seed=0, n_points=40000)
+    scan['feats'] = scan['feats'][:, :1].copy()  # intensity only
+    torch.manual_seed(0)
+    model = SoftGroup(**model_cfg('kitti')).cuda().eval()
+    hb = harness.to_host_batch(scan)
+    inj = harness.pointwise_injection(scan, sigma=0.05, seed=0)
+    with torch.no_grad():
+        ret = harness.run_scan(model, hb, inject_pointwise=inj)
+    assert 'panoptic_preds' in ret and ret['panoptic_preds'].shape == (40000, )
+    assert ret['panoptic_preds'].dtype == np.uint32
+    pp = ret['panoptic_preds']
+    sem = pp & 0xFFFF
+    ids = pp >> 16
+    assert sem.max() <= 19
+    # things with an id carry a thing class (>= 11), stuff carries id 0 (softgroup.py:632-638)
+    assert np.all(sem[ids > 0] >= 11)
+
+
+def test_panoptic_fusion_matches_direct_restatement():
+    from softgroup_b200.util import rle_encode
+    rng = np.random.RandomState(1)
+    model = SoftGroup(**model_cfg('kitti')).eval()
+    N = 500
+    sem = rng.randint(0, 19, N)
+    insts = []
+    for k in range(12):
+        m = (rng.rand(N) < 0.1).astype(np.int64)
+        insts.append(dict(scan_id='s', label_id=int(rng.randint(1, 9)), conf=float(rng.rand()), pred_mask=rle_encode(m),
+                          _m=m.astype(bool)))
+    got = model.panoptic_fusion(sem, insts)
+    # direct restatement: highest confidence first, skip if > 50 % already covered, paste the uncovered part
+    cls_off = 19 - 8 - 1
+    pc, pid = sem.astype(np.uint32).copy(), np.zeros(N, np.uint32)
+    covered = np.zeros(N, bool)
+    nid = 1
+    for k in np.argsort([x['conf'] for x in insts])[::-1]:
+        m = insts[k]['_m']
+        if (m & covered).sum() / (m.sum() + 1e-5) > 0.5:
+            continue
+        paste = m & ~covered
+        pc[paste] = insts[k]['label_id'] + cls_off
+        pid[paste] = nid
+        covered |= paste
+        nid += 1
+    want = (pc & 0xFFFF) | (pid << 16)
+    want[(pc >= 11) & (pid == 0)] = 19
+    assert np.array_equal(got, want.astype(np.uint32))
