@@ -98,6 +98,21 @@ int sgb_ballquery_batch_p_async(int n, long long capacity, float radius, const f
                                 int32_t *d_start_len, int32_t *d_total, void *d_ws, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Octree ball query (SoftGroup++) -- replaces build_and_export_octree (octree_ball_query/octree_ball_query.cpp:150-165,
+ * CPU pointer tree) and octree_ball_query (octree_ball_query.cu:128-147). Fixed 3 levels: boxes f32 [585,6] in BFS
+ * order from xyzwhl = (centre, extent) f32 [6]; pt_inds int32 [n] (leaf-major, ascending inside a leaf);
+ * pt_start_len int32 [512,2]. Query: neighbours in LEAF-MAJOR order, first 1000 kept; d_out_inds has capacity
+ * n*mean_active with the reference's truncation; returns (blocking) the total count, like the reference.
+ * The tree ignores batch indices (batch size 1 only), like the reference.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_octree_workspace_bytes(int n);
+int sgb_octree_build(const float *d_points, int n, const float *d_xyzwhl, float *d_boxes, int32_t *d_pt_inds,
+                     int32_t *d_pt_start_len, void *d_ws, size_t ws_bytes, void *stream);
+long long sgb_octree_ball_query(const float *d_points, const float *d_boxes, const int32_t *d_pt_inds,
+                                const int32_t *d_pt_start_len, int n, int mean_active, float radius, int32_t *d_out_inds,
+                                int32_t *d_out_start_len, int32_t *d_total, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * bfs_cluster -- replaces bfs_cluster / get_clusters / find_cc / fill_cluster_idxs_
  * (bfs_cluster/bfs_cluster.cpp:33-126), on the GPU, bit-exact including BFS visitation order.
  * d_ball_query_idxs int32 [nActive], d_start_len int32 [N,2] (DEVICE memory; the reference takes CPU

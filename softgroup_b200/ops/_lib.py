@@ -31,6 +31,9 @@ SIGNATURES = {
     'sgb_ballquery_batch_p': (c_longlong, [c_int, c_int, c_float, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     'sgb_ballquery_batch_p_async': (c_int, [c_int, c_longlong, c_float, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                             _P]),
+    'sgb_octree_workspace_bytes': (c_size_t, [c_int]),
+    'sgb_octree_build': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'sgb_octree_ball_query': (c_longlong, [_P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P]),
     'sgb_bfs_cluster_workspace_bytes': (c_size_t, [c_int]),
     'sgb_bfs_cluster_count': (c_int, [_P, _P, c_int, c_float, _P, _P, c_int, _P, c_size_t, _INTP, _INTP, _P]),
     'sgb_bfs_cluster_scratch_bytes': (c_size_t, [c_int, c_int]),

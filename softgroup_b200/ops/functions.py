@@ -46,9 +46,49 @@ def ball_query(coords, batch_idxs, batch_offsets, radius, mean_active, with_octr
     return ballquery_batch_p(coords, batch_idxs, batch_offsets, radius, mean_active)
 
 
+def build_octree(coords):
+    """functions.py:14-29 of the reference, on the GPU: (boxes f32 [585,6], pt_inds i32 [n], pt_start_len i32 [512,2])."""
+    L = _lib.lib()
+    coords = _cuda(coords).contiguous()
+    dev = coords.device
+    n = coords.size(0)
+    xyz_max = coords.max(0)[0]
+    xyz_min = coords.min(0)[0]
+    xyzwhl = torch.cat([(xyz_max + xyz_min) / 2, xyz_max - xyz_min]).contiguous()
+    boxes = torch.empty((585, 6), dtype=torch.float32, device=dev)
+    pt_inds = torch.empty(n, dtype=torch.int32, device=dev)
+    pt_start_len = torch.empty((512, 2), dtype=torch.int32, device=dev)
+    ws = _ws(L.sgb_octree_workspace_bytes(n), dev)
+    with profiler.record('octree_build', 12 * n + 4 * n + 585 * 24 + 4096):
+        check(L.sgb_octree_build(ptr(coords), n, ptr(xyzwhl), ptr(boxes), ptr(pt_inds), ptr(pt_start_len), ptr(ws),
+                                 ws.numel(), _stream()), 'sgb_octree_build')
+    return boxes, pt_inds, pt_start_len
+
+
 def octree_ball_query(coords, mean_active, radius):
-    """functions.py:14-44 of the reference (SoftGroup++). Not built yet: fail loudly, never fall back."""
-    raise NotImplementedError('octree_ball_query is scheduled after the SoftGroup (non ++) path; see DESIGN.md')
+    """functions.py:14-44 of the reference (SoftGroup++): leaf-major neighbour order, first 1000 kept."""
+    L = _lib.lib()
+    coords = _cuda(coords).contiguous()
+    assert coords.is_contiguous()
+    dev = coords.device
+    n = coords.size(0)
+    boxes, pt_inds, pt_start_len = build_octree(coords)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    mean_active = int(mean_active)
+    while True:
+        out_inds = torch.empty(max(n * mean_active, 1), dtype=torch.int32, device=dev)
+        out_start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        rec = profiler.record('octree_ball_query')
+        with rec:
+            n_totals = check(
+                L.sgb_octree_ball_query(ptr(coords), ptr(boxes), ptr(pt_inds), ptr(pt_start_len), n, mean_active,
+                                        float(radius), ptr(out_inds), ptr(out_start_len), ptr(total), _stream()),
+                'sgb_octree_ball_query')
+            rec.nbytes = 24 * n + 585 * 24 + 4 * n + 4096 + 4 * min(n_totals, n * mean_active)
+        if n_totals <= n * mean_active:
+            break
+        mean_active = int(n_totals // n + 1)
+    return out_inds[:n_totals], out_start_len
 
 
 class BallQueryBatchP(Function):

@@ -323,3 +323,26 @@ def test_mask_iou_and_label():
     iou = a.cpu().numpy()
     m = ops.get_mask_label(_cuda(pidx), _cuda(off), _cuda(labels), _cuda(cls), _cuda(pointnum), a, 0.02)
     assert np.array_equal(m.cpu().numpy(), oracle.get_mask_label(pidx, off, labels, cls, pointnum, iou, 0.02))
+
+
+# ------------------------------------------------------------------ octree ball query (SoftGroup++)
+def test_octree_build_golden(golden):
+    boxes, pt_inds, psl = ops.build_octree(_cuda(golden['oct_pts']))
+    assert np.array_equal(boxes.cpu().numpy(), golden['oct_boxes'])
+    assert np.array_equal(pt_inds.cpu().numpy(), golden['oct_pt_inds'])
+    assert np.array_equal(psl.cpu().numpy(), golden['oct_psl'])
+
+
+@pytest.mark.parametrize('n,r,scale', [(3000, 0.15, (3., 2., 1.)), (20000, 0.05, (2., 2., 0.5)), (1, 0.1, (1., 1., 1.)),
+                                       (6000, 0.6, (1., 1., 1.))])
+def test_octree_ball_query_vs_oracle(n, r, scale):
+    rng = np.random.RandomState(n)
+    pts = (rng.rand(n, 3) * np.array(scale)).astype(np.float32)
+    boxes, pt_inds, psl = ops.build_octree(_cuda(pts))
+    ob, oi, op = oracle.build_octree(pts)
+    assert np.array_equal(boxes.cpu().numpy(), ob) and np.array_equal(pt_inds.cpu().numpy(), oi)
+    assert np.array_equal(psl.cpu().numpy(), op)
+    idx, sl = ops.octree_ball_query(_cuda(pts), 20, r)
+    oidx, osl = oracle.octree_ball_query(pts, 20, r)
+    assert idx.numel() == oidx.size
+    _assert_lists_equal(_lists(idx, sl), _lists(oidx, osl))  # leaf-major order, cap 1000 (n=6000, r=0.6 hits it)
