@@ -40,9 +40,22 @@ _KITTI = dict(  # configs/softgroup/softgroup_kitti.yaml:1-31
                   panoptic_skip_iou=0.5),
     fixed_modules=[])
 
-CONFIGS = {'scannet': _SCANNET, 's3dis': _S3DIS, 'kitti': _KITTI}
+_STPLS3D_PP = dict(  # configs/softgroup++/softgroup++_stpls3d.yaml:1-37 (lvl_fusion sits under train_cfg there: unused at test)
+    channels=16, num_blocks=7, semantic_classes=15, instance_classes=14, sem2ins_classes=[], semantic_only=False,
+    ignore_label=-100, with_coords=False,
+    grouping_cfg=dict(score_thr=0.2, radius=0.9, mean_active=3,
+                      class_numpoint_mean=[-1., 10408., 58., 124., 1351., 162., 430., 1090., 451., 26., 43., 61., 39., 109.,
+                                           1239],
+                      npoint_thr=0.01, ignore_classes=[0], with_pyramid=True, pyramid_base_size=0.3333, with_octree=True),
+    instance_voxel_cfg=dict(scale=3, spatial_shape=20),
+    train_cfg=dict(max_proposal_num=200, pos_iou_thr=0.5),
+    test_cfg=dict(x4_split=False, cls_score_thr=0.001, mask_score_thr=-0.5, min_npoint=10,
+                  eval_tasks=['semantic', 'instance']),
+    fixed_modules=[])
+
+CONFIGS = {'scannet': _SCANNET, 's3dis': _S3DIS, 'kitti': _KITTI, 'stpls3d++': _STPLS3D_PP}
 # which synthetic shape (softgroup_b200.synth.SHAPES) goes with which config
-SHAPE_OF = {'scannet': 'c2_scannet', 's3dis': 'c3_s3dis', 'kitti': 'c4_kitti'}
+SHAPE_OF = {'scannet': 'c2_scannet', 's3dis': 'c3_s3dis', 'kitti': 'c4_kitti', 'stpls3d++': 'c5_stpls3d'}
 
 
 def model_cfg(name='scannet', **overrides):

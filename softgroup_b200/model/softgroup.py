@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import spconv
-from ..ops import (ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
+from ..ops import (ball_query, ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
                    voxelization_idx)
 from ..util import cuda_cast, force_fp32, rle_encode_ids
 from .blocks import MLP, ResidualBlock, UBlock
@@ -268,8 +268,8 @@ class SoftGroup(nn.Module):
         mean_active = int(self._cfg(g, 'mean_active'))
         npoint_thr = float(self._cfg(g, 'npoint_thr'))
         score_thr = float(self._cfg(g, 'score_thr'))
-        assert not self._cfg(g, 'with_pyramid', False) and not self._cfg(g, 'with_octree', False), \
-            'SoftGroup++ grouping (pyramid/octree) is not built yet'
+        if self._cfg(g, 'with_pyramid', False) or self._cfg(g, 'with_octree', False):
+            return self._forward_grouping_pp(scores, pt_offsets, batch_idxs, coords_float, batch_size)
         cnm = self._cfg(g, 'class_numpoint_mean')
         assert len(cnm) == self.semantic_classes
         ignore = set(self._cfg(g, 'ignore_classes', []))
@@ -308,6 +308,108 @@ class SoftGroup(nn.Module):
         # proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1]] (:464)
         cidx[:, 1] = pts[cidx[:, 1].long()].int()
         return cidx, coff
+
+    # ------------------------------------------------------------------------------------------------------
+    def _forward_grouping_pp(self, scores, pt_offsets, batch_idxs, coords_float, batch_size):
+        """SoftGroup++ grouping (softgroup.py:427-463, 482-507): per class, optional pyramid re-voxelisation at
+        base_size*level, octree ball query, clustering, inverse pyramid map -- every step on the GPU (the reference
+        hashes on the CPU at :494 and builds a dense [nCluster, n] CPU matrix at :500-507). The radius and the level
+        depend on the class size, so classes stay separate launches here."""
+        g = self.grouping_cfg
+        dev = scores.device
+        base_radius = float(self._cfg(g, 'radius'))
+        mean_active = int(self._cfg(g, 'mean_active'))
+        npoint_thr = float(self._cfg(g, 'npoint_thr'))
+        score_thr = float(self._cfg(g, 'score_thr'))
+        with_pyramid = self._cfg(g, 'with_pyramid', False)
+        with_octree = self._cfg(g, 'with_octree', False)
+        base_size = self._cfg(g, 'pyramid_base_size', 0.02)
+        cnm = self._cfg(g, 'class_numpoint_mean')
+        ignore = set(self._cfg(g, 'ignore_classes', []))
+        min_npoint = int(self._cfg(self.test_cfg, 'min_npoint', 0))
+        radius = base_radius
+        idx_list, off_list = [], []
+        n_prop, n_pts = 0, 0
+        for class_id in range(self.semantic_classes):
+            if class_id in ignore:
+                continue
+            object_idxs = (scores[:, class_id] > score_thr).nonzero().view(-1)
+            if object_idxs.size(0) < min_npoint:
+                continue
+            batch_idxs_ = batch_idxs[object_idxs].int()
+            coords_ = coords_float[object_idxs]
+            pt_offsets_ = pt_offsets[object_idxs]
+            l2p_map = None
+            if with_pyramid:
+                level = self.get_level(coords_.size(0))
+                radius = base_radius * level
+                coords_, pt_offsets_, batch_idxs_, l2p_map = self.pyramid_map(coords_, pt_offsets_, batch_idxs_, level,
+                                                                              base_size)
+            batch_offsets_ = self.get_batch_offsets(batch_idxs_, batch_size)
+            neighbor_inds, start_len = ball_query((coords_ + pt_offsets_).contiguous(), batch_idxs_.contiguous(),
+                                                  batch_offsets_, radius, mean_active, with_octree=with_octree)
+            thr = npoint_thr if cnm[class_id] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[class_id]))
+            if neighbor_inds.numel() == 0:
+                neighbor_inds = torch.zeros(1, dtype=torch.int32, device=dev)
+            pidx, poff = bfs_cluster_segments(neighbor_inds.contiguous(), start_len, thr)
+            if l2p_map is not None:
+                pidx, poff = self.pyramid_inverse_map(pidx, poff, coords_.size(0), l2p_map)
+            if pidx.size(0) == 0:
+                continue
+            pidx = pidx.clone()
+            pidx[:, 1] = object_idxs[pidx[:, 1].long()].int()
+            pidx[:, 0] += n_prop
+            idx_list.append(pidx)
+            off_list.append(poff[1:] + n_pts if off_list else poff)
+            n_prop += poff.numel() - 1
+            n_pts += pidx.size(0)
+        if not idx_list:
+            return (torch.zeros((0, 2), dtype=torch.int32, device=dev), torch.zeros((0, ), dtype=torch.int32, device=dev))
+        return torch.cat(idx_list, 0).contiguous(), torch.cat(off_list).int().contiguous()
+
+    def get_level(self, num_points):
+        """softgroup.py:482-489."""
+        if num_points > 1000000:
+            return 3
+        if num_points > 100000:
+            return 2
+        return 1
+
+    def get_batch_offsets(self, batch_idxs, bs):
+        """softgroup.py:711-716 without the per-batch host sync loop."""
+        counts = torch.bincount(batch_idxs.long(), minlength=bs)
+        off = torch.zeros(bs + 1, dtype=torch.int32, device=batch_idxs.device)
+        off[1:] = counts.cumsum(0).int()
+        return off
+
+    def pyramid_map(self, coords_float, pt_offsets, batch_idxs, level=1, base_size=0.02):
+        """softgroup.py:491-498, hash on the GPU. Returns level-voxel coords/offsets (means), their batch index and
+        the point->level-voxel map."""
+        coords = (coords_float / (base_size * level)).long()
+        coords = torch.cat([batch_idxs[:, None].long(), coords], dim=1).contiguous()
+        n_batch = int(batch_idxs[-1].item()) + 1
+        vcoords, l2p_map, p2l_map = voxelization_idx(coords, n_batch)
+        coords_float = voxelization(coords_float.contiguous(), p2l_map)
+        pt_offsets = voxelization(pt_offsets.contiguous(), p2l_map)
+        return coords_float, pt_offsets, vcoords[:, 0].int().contiguous(), l2p_map
+
+    def pyramid_inverse_map(self, proposals_idx, proposals_offset, num_points, l2p_map):
+        """softgroup.py:500-507 without the dense [nCluster, n] matrix: every level-voxel belongs to at most one
+        cluster, so each point inherits the cluster of its voxel; pairs come out sorted by (cluster, point) exactly like
+        `nonzero()` of the dense matrix."""
+        dev = l2p_map.device
+        n_cluster = proposals_offset.numel() - 1
+        vox_cluster = torch.full((num_points, ), -1, dtype=torch.int64, device=dev)
+        vox_cluster[proposals_idx[:, 1].long()] = proposals_idx[:, 0].long()
+        c_of_point = vox_cluster[l2p_map.long()]
+        pts = (c_of_point >= 0).nonzero().view(-1)
+        c_sel = c_of_point[pts]
+        order = torch.argsort(c_sel, stable=True)
+        out_idx = torch.stack([c_sel[order], pts[order]], 1).int().contiguous()
+        counts = torch.bincount(c_sel, minlength=n_cluster)
+        out_off = torch.zeros(n_cluster + 1, dtype=torch.int32, device=dev)
+        out_off[1:] = counts.cumsum(0).int()
+        return out_idx, out_off
 
     # ------------------------------------------------------------------------------------------------------
     @force_fp32(apply_to='feats')

@@ -213,3 +213,66 @@ def test_panoptic_fusion_matches_direct_restatement():
     want = (pc & 0xFFFF) | (pid << 16)
     want[(pc >= 11) & (pid == 0)] = 19
     assert np.array_equal(got, want.astype(np.uint32))
+
+
+def _grouping_pp_reference(prob, offs, coords_float, cfg, min_npoint):
+    """SoftGroup++ per-class loop (softgroup.py:427-480) restated with oracle ops; batch size 1."""
+    g = cfg['grouping_cfg']
+    mean = np.asarray(g['class_numpoint_mean'], np.float32)
+    idx_list, off_list = [], []
+    for c in range(cfg['semantic_classes']):
+        if c in g['ignore_classes']:
+            continue
+        obj = np.where(prob[:, c] > g['score_thr'])[0]
+        if obj.size < min_npoint:
+            continue
+        cf, po = coords_float[obj], offs[obj]
+        level = 3 if obj.size > 1000000 else 2 if obj.size > 100000 else 1
+        radius = g['radius'] * level
+        size = np.float32(g['pyramid_base_size'] * level)
+        lc = np.trunc(cf / size).astype(np.int64)  # (coords_float / (base_size*level)).long()
+        lc = np.concatenate([np.zeros((obj.size, 1), np.int64), lc], 1)
+        _, l2p, p2l = oracle.voxelization_idx(lc, 1, 4)
+        vcf, vpo = oracle.voxelization(cf, p2l, 4), oracle.voxelization(po, p2l, 4)
+        nidx, sl = oracle.octree_ball_query((vcf + vpo).astype(np.float32), g['mean_active'], radius)
+        pidx, poff = oracle.bfs_cluster(mean, nidx, sl, g['npoint_thr'], c)
+        # pyramid_inverse_map (:500-507): dense matrix, nonzero
+        dense = np.zeros((len(poff) - 1, vcf.shape[0]), np.int32)
+        dense[pidx[:, 0], pidx[:, 1]] = 1
+        dense = dense[:, l2p]
+        nz = np.argwhere(dense)
+        poff = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.int32)
+        pidx = nz.astype(np.int32)
+        pidx[:, 1] = obj[pidx[:, 1]]
+        if off_list:
+            pidx[:, 0] += sum(len(x) for x in off_list) - 1
+            poff = (poff + off_list[-1][-1])[1:]
+        if pidx.shape[0] > 0:
+            idx_list.append(pidx)
+            off_list.append(poff)
+    return np.concatenate(idx_list), np.concatenate(off_list)
+
+
+def test_softgroup_pp_grouping_matches_reference_loop():
+    """SoftGroup++ (STPLS3D config): pyramid re-voxelisation + octree ball query + inverse map, incl. a level-2 class."""
+    cfg = model_cfg('stpls3d++')
+    scan = synth.make_scan('c5_stpls3d', seed=0, n_points=260000)
+    # make one class dominant (> 100k points -> pyramid level 2)
+    sem = scan['semantic_labels'].copy()
+    sem[(scan['instance_labels'] >= 0) & (sem % 2 == 1)] = 1
+    scan['semantic_labels'] = sem
+    scores, offs = synth.grouping_inputs(scan, sigma=0.3, seed=0)
+    torch.manual_seed(0)
+    model = SoftGroup(**cfg).cuda().eval()
+    n = sem.shape[0]
+    with torch.no_grad():
+        sc = torch.from_numpy(scores).cuda()
+        prob = sc.softmax(-1).cpu().numpy()
+        pidx, poff = model.forward_grouping(sc, torch.from_numpy(offs).cuda(),
+                                            torch.zeros(n, dtype=torch.int32, device='cuda'),
+                                            torch.from_numpy(scan['coords_float']).cuda(), None)
+    assert (prob[:, 1] > 0.2).sum() > 100000
+    want_idx, want_off = _grouping_pp_reference(prob, offs, scan['coords_float'], cfg, cfg['test_cfg']['min_npoint'])
+    assert np.array_equal(poff.cpu().numpy(), want_off)
+    assert np.array_equal(pidx.cpu().numpy(), want_idx)
+    assert len(want_off) > 20
