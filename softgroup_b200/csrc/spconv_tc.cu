@@ -16,6 +16,8 @@
 // sequential convolutions rules out plain TF32).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sgb {
@@ -72,7 +74,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   const int N = p.N, NT = p.NT;
   const int n0 = blockIdx.y * NT;
   const int nt = min(NT, N - n0);                     // columns of this CTA (multiple of 16)
-  const uint32_t b_bytes = (uint32_t)NT * TC_KC * 4;  // NT * 128 B
+  const uint32_t b_bytes = (uint32_t)NT * TC_KC * 2;  // NT * 64 B (fp16)
   const uint32_t bstage_bytes = 2 * b_bytes;    // weight ring stage: hi + lo
   const int NS = p.nstages, NSB = p.nbstages;   // NS: A stages in TMEM (64 columns each), NSB: weight stages in smem
   unsigned char *bring = smem;
@@ -245,13 +247,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       const int c0 = kc * TC_KC;
       const int kvalid = min(TC_KC, p.Cin - c0);
       // ---- A: registers -> (BN+ReLU) -> hi / lo -> tensor memory (lane = row, column = channel) -----------
-      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 64);
-#pragma unroll
-      for (int hq = 0; hq < 2; hq++) {  // 16 channels at a time keeps the register footprint at two CTAs per SM
+      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
+      {
+        // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): |x - hi - lo| <= 2^-22 |x| (or 2^-25 absolute when lo is
+        // subnormal); two halves per 32-bit TMEM column (channel 2c in the low half). 16 columns hi + 16 columns lo.
         uint32_t hv[16], lv[16];
 #pragma unroll
-        for (int qq = 0; qq < 4; qq++) {
-          const int q = hq * 4 + qq;
+        for (int q = 0; q < 8; q++) {
           float4 x = v[q];
           if (has_act && vsrc >= 0) {
             const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[c0 + 4 * q]);
@@ -267,14 +269,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
               if (4 * q + 3 >= kvalid) x.w = 0.f;
             }
           }
-          const float4 h = tf32_hi(x);
-          hv[4 * qq + 0] = __float_as_uint(h.x); hv[4 * qq + 1] = __float_as_uint(h.y);
-          hv[4 * qq + 2] = __float_as_uint(h.z); hv[4 * qq + 3] = __float_as_uint(h.w);
-          lv[4 * qq + 0] = __float_as_uint(x.x - h.x); lv[4 * qq + 1] = __float_as_uint(x.y - h.y);
-          lv[4 * qq + 2] = __float_as_uint(x.z - h.z); lv[4 * qq + 3] = __float_as_uint(x.w - h.w);
+          const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+          hv[2 * q] = *reinterpret_cast<const uint32_t *>(&h01);
+          hv[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+          lv[2 * q] = *reinterpret_cast<const uint32_t *>(&l01);
+          lv[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&l23);
         }
-        tmem_st16(ta + (uint32_t)(hq * 16), hv);
-        tmem_st16(ta + 32u + (uint32_t)(hq * 16), lv);
+        tmem_st16(ta, hv);
+        tmem_st16(ta + 16u, lv);
       }
       const int s_done = s;
       kc += 2;
@@ -299,8 +303,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
         if (ub >= 1) mbar_wait(smem_u32(&bars[15 + sb]), (uint32_t)((ub - 1) & 1));
         const int o = s_list[a_idx];
         const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
-        const int ksteps = (kvalid + 7) >> 3;
-        const float4 *g = reinterpret_cast<const float4 *>(p.Wp) + ((size_t)o * nkc + kc) * (size_t)N * 16;
+        const int ksteps = (kvalid + 15) >> 4;  // K = 16 halves per tcgen05.mma
+        const float4 *g = reinterpret_cast<const float4 *>(p.Wp) + ((size_t)o * nkc + kc) * (size_t)N * 8;
         const uint32_t bb = smem_u32(bring + (size_t)sb * bstage_bytes);
         const uint32_t bar = smem_u32(&bars[10 + sb]);
         const int nseg = 4 * ksteps;  // (chunk, part) segments of nt*16 bytes
@@ -328,8 +332,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
     //      so columns [0,nt) hold hi*hi and [nt,2nt) the two correction products (summed in the epilogue).
     //      Descriptors are advanced by adding constants to their low word; the issue loop is kept minimal because
     //      a single thread's instruction stream paces the tensor pipe (measured ~50 cycles / tcgen05.mma at N<=64).
-    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * nt) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+    // instruction descriptor: D = f32 (1 << 4), A = B = f16 (format 0), both K-major, N >> 3, M >> 4
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * nt) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
     const uint32_t b_lbo = (uint32_t)(2 * nt) * 16;
     const uint64_t b_step = (uint64_t)((2 * b_lbo) >> 4);
     uint32_t first = 0u;  // 0 for the very first MMA (overwrite), then 1
@@ -344,23 +349,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       if (dbg_on) p.dbg[i * 8 + 6] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
-      const int ksteps = (kvalid + 7) >> 3;
+      const int ksteps = (kvalid + 15) >> 4;
       const uint32_t sbt = smem_u32(bring + (size_t)sb * bstage_bytes);
       uint64_t dbb = umma_desc(sbt, b_lbo, 128);
-      uint32_t ah = tmem + (uint32_t)(p.tmem_acols + s * 64), al = ah + 32u;
-      if (ksteps == 4) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-          umma_tf32_ts(tmem, ah, dbb, idesc2, (ks == 0) ? first : 1u);
-          umma_tf32_ts(tmem + (uint32_t)nt, al, dbb, idesc1, 1u);
-          ah += 8u; al += 8u; dbb += b_step;
-        }
-      } else {
-        for (int ks = 0; ks < ksteps; ks++) {
-          umma_tf32_ts(tmem, ah, dbb, idesc2, (ks == 0) ? first : 1u);
-          umma_tf32_ts(tmem + (uint32_t)nt, al, dbb, idesc1, 1u);
-          ah += 8u; al += 8u; dbb += b_step;
-        }
+      uint32_t ah = tmem + (uint32_t)(p.tmem_acols + s * 32), al = ah + 16u;
+      for (int ks = 0; ks < ksteps; ks++) {
+        umma_tf32_ts(tmem, ah, dbb, idesc2, (ks == 0) ? first : 1u);
+        umma_tf32_ts(tmem + (uint32_t)nt, al, dbb, idesc1, 1u);
+        ah += 8u; al += 8u; dbb += b_step;
       }
       first = 1u;
       umma_commit(smem_u32(&bars[4 + s]));    // frees the A stage once the MMAs above have read it
@@ -435,7 +431,7 @@ void sgb_test_set_tc_debug(long long *d_buf) { g_tc_dbg = d_buf; }
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout) {
   int N = (Cout + 15) / 16 * 16;
   int nkc = (Cin + 31) / 32;
-  return (long long)K * nkc * 8 * 2 * N * 4;
+  return (long long)K * nkc * 4 * 2 * N * 4;  // fp16: 4 chunks of 8 halves, counted in 32-bit words
 }
 
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
@@ -470,14 +466,14 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
     NT = nxt;
   }
   p.NT = NT;
-  size_t bstage = 2 * (size_t)NT * TC_KC * 4;      // weight ring stage (hi + lo) in shared memory
+  size_t bstage = 2 * (size_t)NT * TC_KC * 2;      // weight ring stage (fp16 hi + lo) in shared memory
   size_t map_bytes = d_map ? (size_t)K * TC_ROWS * 4 : 0;
   // TMEM budget: accumulator [main | corrections] = 2*NT columns, then the A ring (64 columns per stage: hi + lo).
   // 256 columns (two CTAs per SM) when that leaves >= 2 A stages, else all 512.
   int dcols = 2 * NT;
   int acols0 = (dcols + 31) / 32 * 32;
-  if (acols0 + 2 * 64 <= 256) { p.tmem_cols = 256; p.nstages = (256 - acols0) / 64; }
-  else { p.tmem_cols = 512; p.nstages = (512 - acols0) / 64; }
+  if (acols0 + 2 * 32 <= 256) { p.tmem_cols = 256; p.nstages = (256 - acols0) / 32; }
+  else { p.tmem_cols = 512; p.nstages = (512 - acols0) / 32; }
   p.nstages = std::min(p.nstages, 4);
   p.tmem_acols = acols0;
   p.nbstages = (int)std::max<size_t>(2, std::min<size_t>(4, (96 * 1024 - map_bytes) / bstage));

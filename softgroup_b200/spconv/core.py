@@ -143,16 +143,18 @@ CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores
 
 
 def pack_weight_tc(W):
-    """[K, Cin, Cout] f32 -> packed [K, nkc, 8, 2, N, 4] for sgb_spconv_forward_tc (layout in sgb200.h)."""
+    """[K, Cin, Cout] f32 -> packed fp16 split for sgb_spconv_forward_tc (layout in sgb200.h):
+    [K, nkc, 4 chunks, 2 (hi, lo), N, 8 halves], hi = fp16(W), lo = fp16(W - hi); returned as a float32-typed buffer."""
     K, Cin, Cout = W.shape
     N = (Cout + 15) // 16 * 16
     nkc = (Cin + 31) // 32
     Wp = torch.zeros((K, nkc * 32, N), dtype=torch.float32, device=W.device)
     Wp[:, :Cin, :Cout] = W
-    Wp = Wp.view(K, nkc, 8, 4, N).permute(0, 1, 2, 4, 3).contiguous()  # [K, nkc, 8, N, 4]
-    hi = (Wp.view(torch.int32) & -8192).view(torch.float32)  # clear the low 13 mantissa bits (TF32-exact)
-    lo = Wp - hi
-    return torch.stack([hi, lo], dim=3).contiguous()  # [K, nkc, 8, 2, N, 4]
+    Wp = Wp.view(K, nkc, 4, 8, N).permute(0, 1, 2, 4, 3).contiguous()  # [K, nkc, 4, N, 8]
+    hi = Wp.half()
+    lo = (Wp - hi.float()).half()
+    packed = torch.stack([hi, lo], dim=3).contiguous()  # [K, nkc, 4, 2, N, 8] fp16
+    return packed.view(torch.float32)
 
 
 class WeightPack(object):
