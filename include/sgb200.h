@@ -208,7 +208,12 @@ long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout);
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
                           const float *d_Wp, int Cin, int Cout, const float *d_in_scale, const float *d_in_shift,
                           const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
-                          int out_stride, int out_off, void *stream);
+                          int out_stride, int out_off, int in_packed, void *stream);
+/* Activation + split, once per tensor instead of once per gathered (row, offset): y = relu?(x*scale+shift) (or x when
+ * scale is NULL) written as packed fp16 hi/lo words, d_y f32-typed [M, ceil(C/32)*32]: per 32-channel chunk 16 words of
+ * hi pairs then 16 words of lo pairs. Feed to sgb_spconv_forward_tc with in_packed = 1 (in_stride = ceil(C/32)*32). */
+int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
+                  float *d_y, int M, int C, void *stream);
 
 /* y[i, c] = max(x[i, c]*scale[c] + shift[c], 0) (relu != 0) -- BatchNorm1d(eval)+ReLU over rows. */
 int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const float *d_shift, int relu, float *d_y,

@@ -37,6 +37,7 @@ struct TcArgs {
   const float *bias;
   float *out; int out_stride, out_off;
   int nstages, nbstages, tmem_cols, tmem_acols;  // A ring depth (TMEM), weight ring depth (smem), TMEM columns, first A column
+  int in_packed;   // input rows are already activated + split: per 32-channel chunk [16 words hi pairs | 16 words lo pairs]
   long long *dbg;  // optional timeline buffer (test hook)
 };
 
@@ -103,6 +104,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // upper half <- first source
+  return *reinterpret_cast<__half2 *>(&r);
 }
 __device__ __forceinline__ float4 tf32_hi(float4 v) {
   float4 h;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       const int kvalid = min(TC_KC, p.Cin - c0);
       vsrc = p.map ? map_s[o * TC_ROWS + r] : (row_ok ? my_row : -1);
       const float *rp = (vsrc >= 0) ? p.in + (size_t)vsrc * p.in_stride + p.in_off + c0 : nullptr;
-      const bool fast = (vsrc >= 0) && vec_ok && (kvalid == TC_KC);
+      const bool fast = (vsrc >= 0) && vec_ok && (kvalid == TC_KC || p.in_packed);
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -248,7 +254,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       const int kvalid = min(TC_KC, p.Cin - c0);
       // ---- A: registers -> (BN+ReLU) -> hi / lo -> tensor memory (lane = row, column = channel) -----------
       const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
-      {
+      if (p.in_packed) {
+        // rows were activated (BatchNorm+ReLU) and split once by sgb_act_split: 128 B per chunk = 16 words of hi pairs
+        // followed by 16 words of lo pairs -> the gather is pure data movement into tensor memory
+        uint32_t w[32];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          w[4 * q + 0] = __float_as_uint(v[q].x); w[4 * q + 1] = __float_as_uint(v[q].y);
+          w[4 * q + 2] = __float_as_uint(v[q].z); w[4 * q + 3] = __float_as_uint(v[q].w);
+        }
+        tmem_st32(ta, w);
+      } else {
         // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): |x - hi - lo| <= 2^-22 |x| (or 2^-25 absolute when lo is
         // subnormal); two halves per 32-bit TMEM column (channel 2c in the low half). 16 columns hi + 16 columns lo.
         uint32_t hv[16], lv[16];
@@ -269,9 +285,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
               if (4 * q + 3 >= kvalid) x.w = 0.f;
             }
           }
-          const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+          const __half2 h01 = f2h2_sat(x.x, x.y), h23 = f2h2_sat(x.z, x.w);
           const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+          const __half2 l01 = f2h2_sat(x.x - f01.x, x.y - f01.y), l23 = f2h2_sat(x.z - f23.x, x.w - f23.y);
           hv[2 * q] = *reinterpret_cast<const uint32_t *>(&h01);
           hv[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&h23);
           lv[2 * q] = *reinterpret_cast<const uint32_t *>(&l01);
@@ -421,11 +437,52 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
 
 using namespace sgb;
 
+namespace sgb {
+// y = BatchNorm(eval)+ReLU(x) (or x when scale == nullptr), split into fp16 hi/lo and packed for the tensor-core
+// kernel: per row and per 32-channel chunk, 16 words of hi pairs (channel 2c in the low half) then 16 words of lo
+// pairs. One thread per (row, chunk, word pair); channels past C are zero.
+__global__ void act_split_kernel(const float *__restrict__ x, int x_stride, int x_off, const float *__restrict__ scale,
+                                 const float *__restrict__ shift, int relu, uint32_t *__restrict__ y, int M, int C, int Cpad) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int wpr = Cpad >> 1;  // word pairs (2 channels) per row
+  if (t >= (long long)M * wpr) return;
+  const int row = (int)(t / wpr), pr = (int)(t % wpr);
+  const int c = 2 * pr;  // first channel of the pair
+  float a = 0.f, b = 0.f;
+  if (c < C) a = x[(size_t)row * x_stride + x_off + c];
+  if (c + 1 < C) b = x[(size_t)row * x_stride + x_off + c + 1];
+  if (scale) {
+    if (c < C) a = fmaf(a, __ldg(&scale[c]), __ldg(&shift[c]));
+    if (c + 1 < C) b = fmaf(b, __ldg(&scale[c + 1]), __ldg(&shift[c + 1]));
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+  }
+  const __half2 h = f2h2_sat(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = f2h2_sat(a - hf.x, b - hf.y);
+  const int chunk = c >> 5, w = (c & 31) >> 1;  // word index inside the chunk's hi block
+  uint32_t *yr = y + (size_t)row * Cpad + chunk * 32;
+  yr[w] = *reinterpret_cast<const uint32_t *>(&h);
+  yr[16 + w] = *reinterpret_cast<const uint32_t *>(&l);
+}
+}  // namespace sgb
+
 static long long *g_tc_dbg = nullptr;
 
 extern "C" {
 
 void sgb_test_set_tc_debug(long long *d_buf) { g_tc_dbg = d_buf; }
+
+int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
+                  float *d_y, int M, int C, void *stream) {
+  if (M == 0 || C == 0) return SGB_OK;
+  SGB_REQUIRE(d_x && d_y && M > 0 && C > 0 && (d_scale == nullptr) == (d_shift == nullptr), SGB_ERR_ARG, "act_split arguments");
+  int Cpad = (C + 31) / 32 * 32;
+  long long tot = (long long)M * (Cpad / 2);
+  act_split_kernel<<<div_up(tot, 256), 256, 0, (cudaStream_t)stream>>>(d_x, x_stride, x_off, d_scale, d_shift, relu,
+                                                                     (uint32_t *)d_y, M, C, Cpad);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
 
 // Packed weight size in floats for sgb_spconv_forward_tc: K * ceil(Cin/32) * 8 * N * 4 with N = Cout rounded to 16.
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout) {
@@ -437,13 +494,15 @@ long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout) {
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
                           const float *d_Wp, int Cin, int Cout, const float *d_in_scale,
                           const float *d_in_shift, const float *d_residual, int res_stride, int res_off,
-                          const float *d_bias, float *d_out, int out_stride, int out_off, void *stream) {
+                          const float *d_bias, float *d_out, int out_stride, int out_off, int in_packed, void *stream) {
   if (Mout == 0 || Cout == 0) return SGB_OK;
+  SGB_REQUIRE(!in_packed || (d_in_scale == nullptr && (in_stride & 31) == 0 && (in_off & 31) == 0), SGB_ERR_ARG,
+              "packed input: no scale/shift, row stride and offset multiples of 32 words");
   SGB_REQUIRE(d_in && d_Wp && d_out && K >= 1 && Mout > 0 && Cin > 0 && Cout > 0, SGB_ERR_ARG,
               "spconv_forward_tc arguments");
   SGB_REQUIRE(d_map || K == 1, SGB_ERR_ARG, "identity map requires K == 1");
   SGB_REQUIRE((d_in_scale == nullptr) == (d_in_shift == nullptr), SGB_ERR_ARG, "scale/shift must come together");
-  SGB_REQUIRE(in_stride >= in_off + Cin && out_stride >= out_off + Cout, SGB_ERR_ARG, "row strides");
+  SGB_REQUIRE((in_packed || in_stride >= in_off + Cin) && out_stride >= out_off + Cout, SGB_ERR_ARG, "row strides");
   int N = (Cout + 15) / 16 * 16;
   SGB_REQUIRE(N <= 256 && Cin <= 512, SGB_ERR_RANGE, "spconv_forward_tc: Cout > 256 or Cin > 512 is not tiled");
   TcArgs p;
@@ -455,6 +514,7 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   p.bias = d_bias;
   p.out = d_out; p.out_stride = out_stride; p.out_off = out_off;
   p.dbg = g_tc_dbg;
+  p.in_packed = in_packed;
   // Column split: few row tiles (deep U-Net levels) would leave most SMs idle and make one CTA stream all the
   // weights, so N is cut into NT-column CTAs until the grid covers the machine (NT multiple of 16, >= 32).
   int tiles = div_up(Mout, TC_ROWS);

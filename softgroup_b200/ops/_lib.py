@@ -53,7 +53,8 @@ SIGNATURES = {
                                    _P, c_int, c_int, _P]),
     'sgb_spconv_tc_packed_floats': (c_longlong, [c_int, c_int, c_int]),
     'sgb_spconv_forward_tc': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, c_int, _P,
-                                      _P, c_int, c_int, _P]),
+                                      _P, c_int, c_int, c_int, _P]),
+    'sgb_act_split': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'sgb_rle_format_ids': (c_longlong, [_P, _P, c_int, _P, c_longlong, _P]),

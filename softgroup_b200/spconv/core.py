@@ -189,12 +189,30 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
         nbytes += 4 * Mout * Cout
     use_tc = CONV_IMPL == 'tc' and Cout <= 256 and Cin <= 512
     name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
+    if use_tc:
+        # activation (+ split into fp16 hi/lo) once per tensor instead of once per gathered (row, offset) in the conv
+        K_eff = K
+        packed_in = None
+        if K_eff > 1 or act is not None:
+            cpad = (Cin + 31) // 32 * 32
+            packed_in = torch.empty((m_in, cpad), dtype=torch.float32, device=feats.device)
+            with profiler.record('act_split', 8 * m_in * Cin):
+                check(
+                    _lib.lib().sgb_act_split(ptr(feats), in_stride, in_off, ptr(scale), ptr(shift), 1, ptr(packed_in), m_in,
+                                             Cin, _stream()), 'sgb_act_split')
     with profiler.record(name, nbytes):
         if use_tc:
-            check(
-                _lib.lib().sgb_spconv_forward_tc(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.tc()), Cin, Cout,
-                                                 ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
-                                                 out_stride, out_off, _stream()), 'sgb_spconv_forward_tc')
+            if packed_in is not None:
+                check(
+                    _lib.lib().sgb_spconv_forward_tc(ptr(packed_in), packed_in.size(1), 0, ptr(mp), K, Mout, ptr(W.tc()),
+                                                     Cin, Cout, None, None, ptr(residual), rs, ro, ptr(bias), ptr(out),
+                                                     out_stride, out_off, 1, _stream()), 'sgb_spconv_forward_tc')
+            else:
+                check(
+                    _lib.lib().sgb_spconv_forward_tc(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.tc()), Cin,
+                                                     Cout, ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias),
+                                                     ptr(out), out_stride, out_off, 0, _stream()),
+                    'sgb_spconv_forward_tc')
         else:
             check(
                 _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.kio), Cin, Cout,
