@@ -214,7 +214,57 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   const int nkc = (p.Cin + TC_KC - 1) / TC_KC;
   const int total = s_nact * nkc;
 
-  if (producer) {
+  if (producer && p.in_packed) {
+    // ---- packed input (activated + split once by sgb_act_split): the gather is pure data movement, so the registers
+    //      freed by the missing transform hold TWO future iterations of this thread's row (4 iterations ahead of the
+    //      MMA warp counting both groups) -- the L2 latency of the gather is covered without shared memory.
+    float4 va[8], vb[8];
+    int ia = 0, ikc = grp;  // issue cursor: (offset list position, channel slice) of the next own iteration to load
+    while (ikc >= nkc) { ikc -= nkc; ia++; }
+    int nload = grp;        // global iteration index of the next load
+    auto load = [&](float4 (&buf)[8]) {
+      if (nload < total) {
+        const int o = s_list[ia];
+        const int src = p.map ? map_s[o * TC_ROWS + r] : (row_ok ? my_row : -1);
+        if (src >= 0) {
+          const float4 *rp = reinterpret_cast<const float4 *>(p.in + (size_t)src * p.in_stride + p.in_off + ikc * TC_KC);
+#pragma unroll
+          for (int q = 0; q < 8; q++) buf[q] = __ldg(rp + q);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; q++) buf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      nload += 2;
+      ikc += 2;
+      while (ikc >= nkc) { ikc -= nkc; ia++; }
+    };
+    int s = grp % NS, u = grp / NS;
+    auto consume = [&](float4 (&buf)[8]) {
+      if (u >= 1) mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((u - 1) & 1));
+      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
+      uint32_t w[32];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        w[4 * q + 0] = __float_as_uint(buf[q].x); w[4 * q + 1] = __float_as_uint(buf[q].y);
+        w[4 * q + 2] = __float_as_uint(buf[q].z); w[4 * q + 3] = __float_as_uint(buf[q].w);
+      }
+      tmem_st32(ta, w);
+      const int s_done = s;
+      s += 2;
+      if (s >= NS) { s -= NS; u++; }
+      load(buf);  // refill this buffer with own-iteration +2 while the store drains
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&bars[s_done]));
+    };
+    load(va);
+    load(vb);
+    for (int i = grp; i < total; i += 4) {
+      consume(va);
+      if (i + 2 < total) consume(vb);
+    }
+  } else if (producer) {
     float4 v[8];
     int vsrc = -1;
     // gather of iteration i into registers (whole 32-channel slice of this thread's row)
@@ -254,17 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       const int kvalid = min(TC_KC, p.Cin - c0);
       // ---- A: registers -> (BN+ReLU) -> hi / lo -> tensor memory (lane = row, column = channel) -----------
       const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
-      if (p.in_packed) {
-        // rows were activated (BatchNorm+ReLU) and split once by sgb_act_split: 128 B per chunk = 16 words of hi pairs
-        // followed by 16 words of lo pairs -> the gather is pure data movement into tensor memory
-        uint32_t w[32];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          w[4 * q + 0] = __float_as_uint(v[q].x); w[4 * q + 1] = __float_as_uint(v[q].y);
-          w[4 * q + 2] = __float_as_uint(v[q].z); w[4 * q + 3] = __float_as_uint(v[q].w);
-        }
-        tmem_st32(ta, w);
-      } else {
+      {
         // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): |x - hi - lo| <= 2^-22 |x| (or 2^-25 absolute when lo is
         // subnormal); two halves per 32-bit TMEM column (channel 2c in the low half). 16 columns hi + 16 columns lo.
         uint32_t hv[16], lv[16];
@@ -414,14 +454,33 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
         const int col = n0 + cb;
         float *op = p.out + (size_t)row * p.out_stride + p.out_off + col;
         const float *rp = p.residual ? p.residual + (size_t)row * p.res_stride + p.res_off + col : nullptr;
+        float x[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-          if (col + e < p.Cout) {
-            float x = __uint_as_float(v[e]);
-            if (p.bias) x += __ldg(&p.bias[col + e]);
-            if (rp) x += __ldg(rp + e);
-            op[e] = x;
+        for (int e = 0; e < 8; e++) x[e] = __uint_as_float(v[e]);
+        const bool full = col + 8 <= p.Cout;
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (col + e < p.Cout) x[e] += __ldg(&p.bias[col + e]);
+        }
+        if (rp) {
+          if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rp)), r1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+            x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+            x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+              if (col + e < p.Cout) x[e] += __ldg(rp + e);
           }
+        }
+        if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+          reinterpret_cast<float4 *>(op)[0] = make_float4(x[0], x[1], x[2], x[3]);
+          reinterpret_cast<float4 *>(op)[1] = make_float4(x[4], x[5], x[6], x[7]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (col + e < p.Cout) op[e] = x[e];
         }
       }
     }
