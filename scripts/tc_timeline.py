@@ -8,7 +8,8 @@ C = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 137000
 rng = np.random.RandomState(0)
 # surface-like sparse set: random voxels on a few planes
-pts = np.unique(np.concatenate([np.stack([np.zeros(M, int), rng.randint(0, 400, M), rng.randint(0, 400, M), rng.randint(0, 3, M) * 40], 1)]), axis=0).astype(np.int32)
+pts = np.unique(np.stack([np.zeros(M, int), rng.randint(0, 300, M), rng.randint(0, 300, M), rng.randint(0, 3, M)], 1), axis=0).astype(np.int32)
+pts = pts[rng.permutation(len(pts))]
 idx = torch.from_numpy(pts).cuda()
 feats = torch.randn(idx.size(0), C, device='cuda')
 conv = spconv.SubMConv3d(C, C, 3, padding=1, bias=False, indice_key='k').cuda()
@@ -26,5 +27,5 @@ print('rows', idx.size(0), 'C', C, 'conv ms', e0.elapsed_time(e1))
 d = dbg.cpu().numpy().reshape(64, 8)
 t0 = d[d > 0].min()
 print('iter: P.wait_start P.wait_done P.sts_done P.fence_done | M.start M.bfull M.afull M.issued   (cycles from start)')
-for i in range(30):
+for i in range(28):
     print(i, ' '.join('%7d' % (v - t0 if v > 0 else -1) for v in d[i]))

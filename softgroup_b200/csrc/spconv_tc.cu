@@ -240,8 +240,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       while (ikc >= nkc) { ikc -= nkc; ia++; }
     };
     int s = grp % NS, u = grp / NS;
+    int dbg_i = grp;
     auto consume = [&](float4 (&buf)[8]) {
+      const bool dbg_on = p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && r == 0 && dbg_i < 64;
+      if (dbg_on) p.dbg[dbg_i * 8 + 0] = clock64();
       if (u >= 1) mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((u - 1) & 1));
+      if (dbg_on) p.dbg[dbg_i * 8 + 1] = clock64();
       const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
       uint32_t w[32];
 #pragma unroll
@@ -253,10 +257,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       const int s_done = s;
       s += 2;
       if (s >= NS) { s -= NS; u++; }
+      if (dbg_on) p.dbg[dbg_i * 8 + 2] = clock64();
       load(buf);  // refill this buffer with own-iteration +2 while the store drains
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (dbg_on) p.dbg[dbg_i * 8 + 3] = clock64();
       mbar_arrive(smem_u32(&bars[s_done]));
+      dbg_i += 2;
     };
     load(va);
     load(vb);
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
     int s = 0, sb = 0, kc = 0;
     uint32_t pa = 0u, pb = 0u;
     for (int i = 0; i < total; i++) {
-      const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && i < 64;
+      const bool dbg_on = p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && i < 64;
       if (dbg_on) p.dbg[i * 8 + 4] = clock64();
       mbar_wait(smem_u32(&bars[10 + sb]), pb);
       if (dbg_on) p.dbg[i * 8 + 5] = clock64();
