@@ -19,9 +19,10 @@
 
 namespace sgb {
 
-constexpr int kBqThreads = 256;
+constexpr int kBqThreads = 1024;
 constexpr int kBqWarps = kBqThreads / 32;
-constexpr int kBqSMax = 8192;  // staged candidates per cell (16 B each, 128 KB)
+constexpr int kBqSMax = 10240;  // staged candidates per cell (16 B each, 160 KB)
+constexpr int kBmWords = 8192;  // index bitmap for the linear-time ordering of a stencil (32 KB + 16 KB prefix)
 constexpr int kCellBias = 131072;
 constexpr int kMaxSeg = 1023;
 
@@ -34,6 +35,8 @@ struct BqWs {
   int32_t *cell_cnt;         // [n] -> scanned in place to starts
   int32_t *slot_of;          // [n]
   float4 *sorted;            // [n] (x,y,z,idx)
+  int32_t *chunk_cell;       // [2n] work item -> cell id
+  int32_t *chunk_q0;         // [2n] work item -> first query of the cell handled by this item
   int32_t *scalars;          // 0: ncells, 1: work counter, 2: error flag, 3: total
   int32_t *scan_tmp;
   uint32_t cap;
@@ -53,6 +56,8 @@ static bool bq_carve(void *ws, size_t bytes, int n, BqWs &w) {
   w.cell_cnt = a.take<int32_t>((size_t)n + 1);
   w.slot_of = a.take<int32_t>((size_t)n + 1);
   w.sorted = a.take<float4>((size_t)n + 1);
+  w.chunk_cell = a.take<int32_t>(2 * (size_t)n + 2);
+  w.chunk_q0 = a.take<int32_t>(2 * (size_t)n + 2);
   w.scan_tmp = a.take<int32_t>(scan_temp_elems((size_t)n + 1));
   return w.scan_tmp != nullptr;
 }
@@ -103,10 +108,21 @@ __global__ void bq_cellcnt_kernel(int n, BqWs w) {
   w.cell_cnt[c] = (c < w.scalars[0]) ? w.slot_cnt[w.cell_slot[c]] : 0;
 }
 
+constexpr int kBqChunk = 128;  // queries per work item: dense cells (hundreds to thousands of queries sharing one
+                              // stencil) are cut into several items so a single SM never owns a whole object core
+
 __global__ void bq_cellstart_kernel(int n, BqWs w) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= w.scalars[0]) return;
-  w.slot_start[w.cell_slot[c]] = w.cell_cnt[c];
+  const int slot = w.cell_slot[c];
+  w.slot_start[slot] = w.cell_cnt[c];
+  const int q = w.slot_cnt[slot];
+  const int nch = (q + kBqChunk - 1) / kBqChunk;
+  const int base = atomicAdd(&w.scalars[4], nch);
+  for (int k = 0; k < nch; k++) {
+    w.chunk_cell[base + k] = c;
+    w.chunk_q0[base + k] = k * kBqChunk;
+  }
 }
 
 __global__ void bq_scatter_kernel(const float *__restrict__ xyz, int n, BqWs w) {
@@ -147,22 +163,24 @@ __global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__res
                                                               int32_t *__restrict__ idx,
                                                               int32_t *__restrict__ start_len, BqWs w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *S = reinterpret_cast<float4 *>(smem_raw);                                   // [kBqSMax]
-  int32_t *stage = reinterpret_cast<int32_t *>(smem_raw + sizeof(float4) * kBqSMax);  // [kBqWarps][1000]
+  float4 *S = reinterpret_cast<float4 *>(smem_raw);  // [kBqSMax]
+  uint32_t *bm = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * kBqSMax);                      // [kBmWords]
+  unsigned short *pre = reinterpret_cast<unsigned short *>(smem_raw + sizeof(float4) * kBqSMax + 4 * kBmWords);  // [kBmWords]
+  __shared__ int s_lo, s_hi, s_wsum[kBqThreads / 32];
   __shared__ int nb_start[27], nb_cnt[27], nb_off[28];
   __shared__ int s_cell;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float r2 = __fmul_rn(radius, radius);
-  const int ncells = w.scalars[0];
-  int32_t *my_stage = stage + warp * SGB_MAX_NEIGHBORS;
+  const int nitems = w.scalars[4];
 
   while (true) {
     __syncthreads();
     if (tid == 0) s_cell = atomicAdd(&w.scalars[1], 1);
     __syncthreads();
-    const int cell = s_cell;
-    if (cell >= ncells) break;
+    const int item = s_cell;
+    if (item >= nitems) break;
+    const int cell = w.chunk_cell[item];
     const int cslot = w.cell_slot[cell];
     const unsigned long long ckey = w.keys[cslot];
     if (tid < 27) {
@@ -188,10 +206,79 @@ __global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__res
     }
     __syncthreads();
     const int total_s = nb_off[27];
-    const int q_start = w.slot_start[cslot], q_cnt = w.slot_cnt[cslot];
+    const int q_first = w.chunk_q0[item];
+    const int q_start = w.slot_start[cslot] + q_first, q_cnt = min(kBqChunk, w.slot_cnt[cslot] - q_first);
 
     if (total_s <= kBqSMax) {
-      // ---- stage the stencil, sort by point index ------------------------------------------------
+      // ---- order the stencil by point index. Point indices are distinct, so the sorted position of a record is
+      //      the number of stencil members with a smaller index: one bit per index in a shared-memory bitmap +
+      //      prefix popcounts gives it in O(|S| + range/32) instead of an O(|S| log^2 |S|) bitonic sort.
+      if (tid == 0) { s_lo = 0x7fffffff; s_hi = -1; }
+      __syncthreads();
+      {
+        int lo = 0x7fffffff, hi = -1;
+        for (int k = 0; k < 27; k++) {
+          int c = nb_cnt[k], st = nb_start[k];
+          for (int t = tid; t < c; t += kBqThreads) {
+            int id = __float_as_int(__ldg(&reinterpret_cast<const float *>(w.sorted + st + t)[3]));
+            lo = min(lo, id);
+            hi = max(hi, id);
+          }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+      }
+      __syncthreads();
+      const int lo = s_lo;
+      const int nwords = (s_hi - lo + 32) >> 5;
+      bool ordered = false;
+      if (nwords <= kBmWords) {
+        for (int t = tid; t < nwords; t += kBqThreads) bm[t] = 0u;
+        __syncthreads();
+        for (int k = 0; k < 27; k++) {
+          int c = nb_cnt[k], st = nb_start[k];
+          for (int t = tid; t < c; t += kBqThreads) {
+            int d = __float_as_int(__ldg(&reinterpret_cast<const float *>(w.sorted + st + t)[3])) - lo;
+            atomicOr(&bm[d >> 5], 1u << (d & 31));
+          }
+        }
+        __syncthreads();
+        {  // exclusive prefix of popcounts: 8 consecutive words per thread
+          const int w0 = tid * 8;
+          int loc[8], sum = 0;
+#pragma unroll
+          for (int e = 0; e < 8; e++) { loc[e] = sum; sum += (w0 + e < nwords) ? __popc(bm[w0 + e]) : 0; }
+          int inc = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t2;
+          }
+          if (lane == 31) s_wsum[warp] = inc;
+          __syncthreads();
+          int woff = 0;
+          for (int q = 0; q < warp; q++) woff += s_wsum[q];
+          const int basep = woff + inc - sum;
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (w0 + e < nwords) pre[w0 + e] = (unsigned short)(basep + loc[e]);
+        }
+        __syncthreads();
+        for (int k = 0; k < 27; k++) {
+          int c = nb_cnt[k], st = nb_start[k];
+          for (int t = tid; t < c; t += kBqThreads) {
+            float4 rec = w.sorted[st + t];
+            int d = __float_as_int(rec.w) - lo;
+            int pos = (int)pre[d >> 5] + __popc(bm[d >> 5] & ((1u << (d & 31)) - 1u));
+            S[pos] = rec;
+          }
+        }
+        __syncthreads();
+        ordered = true;
+      }
+      if (!ordered) {
+      // ---- index range too wide for the bitmap: stage the stencil and bitonic-sort it ---------------------
       int P = 32;
       while (P < total_s) P <<= 1;
       for (int k = 0; k < 27; k++) {
@@ -214,27 +301,48 @@ __global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__res
           __syncthreads();
         }
       }
+      }  // !ordered
       // ---- queries of this cell: one warp each ----------------------------------------------------
       for (int q = warp; q < q_cnt; q += kBqWarps) {
         float4 qp = w.sorted[q_start + q];
         int qi = __float_as_int(qp.w);
-        int cnt = 0;
+        // pass 1: count (first 1000 by index); pass 2: write straight to the reserved global range. The candidates
+        // sit in shared memory, so scanning twice is cheaper than staging 4 KB per warp (which would cap the CTA at
+        // 8 warps and quadruple the per-cell sort time).
+        // the ballot masks of pass 1 are kept in the (now idle) bitmap area, one word per 32 candidates, so pass 2 does
+        // not recompute distances and only touches the index word of actual hits
+        uint32_t *masks = bm + warp * (kBqSMax / 32);
+        int cnt = 0, last = 0;
         for (int b0 = 0; b0 < total_s && cnt < SGB_MAX_NEIGHBORS; b0 += 32) {
           int t = b0 + lane;
           bool hit = false;
-          int ci = 0;
           if (t < total_s) {
             float4 c = S[t];
-            ci = __float_as_int(c.w);
             hit = bq_hit(qp.x, qp.y, qp.z, c.x, c.y, c.z, r2);
           }
-          unsigned m = __ballot_sync(0xffffffffu, hit);
-          int pos = cnt + __popc(m & ((1u << lane) - 1));
-          if (hit && pos < SGB_MAX_NEIGHBORS) my_stage[pos] = ci;
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (lane == 0) masks[b0 >> 5] = m;
           cnt = min(cnt + __popc(m), SGB_MAX_NEIGHBORS);
+          last = b0 + 32;
         }
         __syncwarp();
-        bq_emit(qi, cnt, my_stage, idx, start_len, &w.scalars[3], capacity, lane);
+        int base = 0;
+        if (lane == 0) {
+          base = atomicAdd(&w.scalars[3], cnt);
+          start_len[2 * (size_t)qi] = base;
+          start_len[2 * (size_t)qi + 1] = cnt;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        long long room = capacity - (long long)base;  // reference truncation (bfs_cluster.cu:55-61)
+        int cw = (room <= 0) ? 0 : (((long long)base + cnt >= capacity) ? (int)room : cnt);
+        int done = 0;
+        for (int b0 = 0; b0 < last && done < cw; b0 += 32) {
+          const unsigned m = masks[b0 >> 5];
+          const bool hit = (m >> lane) & 1u;
+          int pos = done + __popc(m & ((1u << lane) - 1));
+          if (hit && pos < cw) idx[(size_t)base + pos] = __float_as_int(S[b0 + lane].w);
+          done += __popc(m);
+        }
         __syncwarp();
       }
     } else {
@@ -244,19 +352,33 @@ __global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__res
         int qi = __float_as_int(qp.w);
         int b = batch_idxs[qi];
         int s0 = batch_offsets[b], e0 = batch_offsets[b + 1];
-        int cnt = 0;
+        int cnt = 0, last = s0;
         for (int b0 = s0; b0 < e0 && cnt < SGB_MAX_NEIGHBORS; b0 += 32) {
           int t = b0 + lane;
           bool hit = false;
           if (t < e0) hit = bq_hit(qp.x, qp.y, qp.z, xyz[3 * (size_t)t], xyz[3 * (size_t)t + 1], xyz[3 * (size_t)t + 2], r2);
-          unsigned m = __ballot_sync(0xffffffffu, hit);
-          int pos = cnt + __popc(m & ((1u << lane) - 1));
-          if (hit && pos < SGB_MAX_NEIGHBORS) my_stage[pos] = t;
-          cnt = min(cnt + __popc(m), SGB_MAX_NEIGHBORS);
+          cnt = min(cnt + __popc(__ballot_sync(0xffffffffu, hit)), SGB_MAX_NEIGHBORS);
+          last = b0 + 32;
         }
-        __syncwarp();
-        bq_emit(qi, cnt, my_stage, idx, start_len, &w.scalars[3], capacity, lane);
-        __syncwarp();
+        int base = 0;
+        if (lane == 0) {
+          base = atomicAdd(&w.scalars[3], cnt);
+          start_len[2 * (size_t)qi] = base;
+          start_len[2 * (size_t)qi + 1] = cnt;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        long long room = capacity - (long long)base;
+        int cw = (room <= 0) ? 0 : (((long long)base + cnt >= capacity) ? (int)room : cnt);
+        int done = 0;
+        for (int b0 = s0; b0 < last && done < cw; b0 += 32) {
+          int t = b0 + lane;
+          bool hit = false;
+          if (t < e0) hit = bq_hit(qp.x, qp.y, qp.z, xyz[3 * (size_t)t], xyz[3 * (size_t)t + 1], xyz[3 * (size_t)t + 2], r2);
+          unsigned m = __ballot_sync(0xffffffffu, hit);
+          int pos = done + __popc(m & ((1u << lane) - 1));
+          if (hit && pos < cw) idx[(size_t)base + pos] = t;
+          done += __popc(m);
+        }
       }
     }
   }
@@ -284,13 +406,13 @@ static int bq_launch(int n, long long capacity, float radius, const float *xyz, 
   SGB_LAUNCH_CHECK();
   bq_scatter_kernel<<<nb, 256, 0, st>>>(xyz, n, w);
   SGB_LAUNCH_CHECK();
-  size_t smem = sizeof(float4) * kBqSMax + sizeof(int32_t) * kBqWarps * SGB_MAX_NEIGHBORS;
+  size_t smem = sizeof(float4) * kBqSMax + 4 * kBmWords + 2 * kBmWords;
   static bool attr_set = false;
   if (!attr_set) {
     SGB_CUDA_CHECK(cudaFuncSetAttribute(bq_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  int grid = std::min(std::max(n, 1), kNumSMs * 2);
+  int grid = std::min(std::max(n, 1), kNumSMs);
   bq_query_kernel<<<grid, kBqThreads, smem, st>>>(xyz, batch_idxs, batch_offsets, n, radius, capacity, idx, start_len, w);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
@@ -306,6 +428,7 @@ size_t sgb_ballquery_workspace_bytes(int n) {
   if (n < 0) n = 0;
   size_t cap = bq_cap(n);
   size_t b = align_up(64 * 4) + align_up(cap * 8) + 3 * align_up(cap * 4) + 3 * align_up(((size_t)n + 1) * 4) +
+             2 * align_up((2 * (size_t)n + 2) * 4) +
              align_up(((size_t)n + 1) * 16) + align_up(scan_temp_elems((size_t)n + 1) * 4);
   return b + 1024;
 }

@@ -346,3 +346,25 @@ def test_octree_ball_query_vs_oracle(n, r, scale):
     oidx, osl = oracle.octree_ball_query(pts, 20, r)
     assert idx.numel() == oidx.size
     _assert_lists_equal(_lists(idx, sl), _lists(oidx, osl))  # leaf-major order, cap 1000 (n=6000, r=0.6 hits it)
+
+
+def test_ballquery_wide_index_range_uses_sort_fallback():
+    # two far-apart index blocks in one dense stencil: index range > 262144 -> bitonic fallback path
+    rng = np.random.RandomState(8)
+    n = 300000
+    xyz = (rng.rand(n, 3) * 40).astype(np.float32)      # sparse background
+    xyz[:300] = (rng.randn(300, 3) * 0.01 + 5).astype(np.float32)    # dense blob, low indices
+    xyz[-300:] = (rng.randn(300, 3) * 0.01 + 5).astype(np.float32)   # same blob, high indices
+    bi = np.zeros(n, np.int32)
+    bo = np.array([0, n], np.int32)
+    idx, sl = ops.ballquery_batch_p(_cuda(xyz), _cuda(bi), _cuda(bo), 0.04, 5)
+    s = sl.cpu().numpy()
+    g = idx.cpu().numpy()
+    for i in list(range(0, 300, 7)) + list(range(n - 300, n, 7)):
+        o = xyz[i]
+        d = xyz - o
+        d2 = (d[:, 1] * d[:, 1]).astype(np.float32)
+        d2 = (d[:, 0].astype(np.float64) * d[:, 0] + d2).astype(np.float32)
+        d2 = (d[:, 2].astype(np.float64) * d[:, 2] + d2).astype(np.float32)
+        want = np.where(d2 < np.float32(0.04) * np.float32(0.04))[0][:1000]
+        assert np.array_equal(g[s[i, 0]:s[i, 0] + s[i, 1]], want), i
