@@ -1,0 +1,71 @@
+"""A/B of the tensor-core conv tunings on the real device step (L2 flushed between steps).
+Usage: tc_tuning_ab.py            -> runs the built-in list of (prefetch, max weight stages, max split-K) settings."""
+import ctypes
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from softgroup_b200 import harness, ops, profiler, synth  # noqa: E402
+from softgroup_b200.configs import model_cfg  # noqa: E402
+from softgroup_b200.model import SoftGroup  # noqa: E402
+from softgroup_b200.ops import _lib  # noqa: E402
+
+L = _lib.lib()
+L.sgb_test_set_tc_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+L.sgb_test_set_tc_tuning.restype = None
+
+torch.manual_seed(0)
+model = SoftGroup(**model_cfg('scannet')).cuda().eval()
+scan = synth.make_scan('c2_scannet', seed=0)
+hb = harness.to_host_batch(scan)
+inj = harness.pointwise_injection(scan, sigma=0.03, seed=0)
+dev = harness.device_batch(hb)
+flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda')
+
+
+def step():
+    vc, v2p, p2v = ops.voxelization_idx(dev['coords'], 1)
+    d = {k: v for k, v in dev.items() if k not in ('coords', 'voxel_coords', 'v2p_map', 'p2v_map')}
+    return model.forward_test(device_only=True, inject_pointwise=inj, voxel_coords=vc, v2p_map=v2p, p2v_map=p2v, **d)
+
+
+def run(tag, pf, nb, sk, steps=8):
+    L.sgb_test_set_tc_tuning(pf, nb, sk)
+    with torch.no_grad():
+        for _ in range(3):
+            out = step()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        profiler.reset()
+        for _ in range(3):
+            flush.zero_()
+            profiler.enable()
+            step()
+            profiler.disable()
+        s = profiler.summary()['by_kernel']
+    conv = {k: v['ms_per_step'] for k, v in s.items() if 'conv' in k or 'linear' in k or 'split' in k}
+    print('%-28s step median %.3f min %.3f ms | %s | proposals %d' %
+          (tag, ms[len(ms) // 2], ms[0], ' '.join('%s=%.3f' % kv for kv in sorted(conv.items())),
+           out['proposals_offset'].numel() - 1), flush=True)
+    return out
+
+
+ref = run('base pf0 pairs3 sk8', 0, 3, 8)
+for tag, pf, nb, sk in [('pf0 pairs2 sk8', 0, 2, 8), ('pf0 pairs3 sk1', 0, 3, 1)]:
+    out = run(tag, pf, nb, sk)
+    for k in ('proposals_idx', 'proposals_offset'):
+        assert torch.equal(out[k], ref[k]), k
+    for k in ('semantic_scores', 'cls_scores', 'mask_scores'):
+        if k in out and k in ref:
+            d = (out[k] - ref[k]).abs().max().item()
+            print('   max |d %s| = %.3g' % (k, d))

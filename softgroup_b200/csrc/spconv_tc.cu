@@ -1,19 +1,26 @@
 // spconv_tc.cu -- sparse convolution on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
-// One CTA owns a tile of 128 output rows x N = Cout columns. For every kernel offset with at least one active
-// pair in the tile and every 32-channel slice of Cin:
-//   * the producer threads gather one input row slice each (eval-BatchNorm + ReLU folded in), split every value into
-//     a TF32-exact high part and an fp32 remainder, and write both straight into TENSOR MEMORY with tcgen05.st
-//     (A operand from TMEM: lane = row, column = channel) -- the shared-memory pipe only carries the weights;
-//   * the pre-packed weight slice (same split, same core-matrix order, done once on the host side) is copied in;
-//   * one thread issues the three error-compensated products hi*hi + hi*lo + lo*hi as
-//     tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Cout, K=8 per instruction) accumulating fp32 in TMEM, then
-//     tcgen05.commit's the shared-memory stage back to the gather threads through an mbarrier.
-// Stages form a ring so gathers of the next slice overlap the MMAs of the previous one. The epilogue reads the
-// accumulator with tcgen05.ld (32 lanes x 32 bit x 16 columns per instruction), adds bias / residual and
-// writes strided rows (the U-Net concat buffer). Dropping the lo*lo term and the TF32 truncation of the
-// remainders leaves a relative error of ~2^-21 per product, i.e. fp32-grade (the north star's 1e-4 over ~40
-// sequential convolutions rules out plain TF32).
+// One CTA owns a tile of 128 output rows x NT <= 128 output columns (and, with split-K, a contiguous share of the
+// (kernel offset, 32-channel slice) iterations). For every kernel offset with at least one active pair in the tile
+// and every 32-channel slice of Cin:
+//   * the producer threads gather one input row slice each. Inputs are either raw fp32 rows (eval-BatchNorm + ReLU
+//     folded in here, then split) or rows already activated and split by sgb_act_split. A value x is carried as
+//     two fp16 numbers hi = fp16(x), lo = fp16(x - hi); both go straight into TENSOR MEMORY with tcgen05.st
+//     (A operand from TMEM: lane = row, 16 columns of hi pairs + 16 columns of lo pairs per stage) -- the
+//     shared-memory pipe only carries the weights;
+//   * the pre-packed weight slice (same split, core-matrix order, done once on the host side) is streamed by one
+//     elected lane with TMA bulk copies into a ring of stages; the weights of the whole convolution are pulled
+//     into L2 with cp.async.bulk.prefetch at kernel start because every CTA walks them in the same order (so they
+//     would otherwise always be cold);
+//   * one thread issues the error-compensated products as tcgen05.mma.cta_group::1.kind::f16 (M=128, K=16)
+//         D[:, 0:2nt]  += A_hi * [B_hi | B_lo]      D[:, nt:2nt] += A_lo * B_hi
+//     accumulating fp32 in TMEM, then tcgen05.commit's the stages back to their producers through mbarriers.
+// The epilogue reads the accumulator with tcgen05.ld, sums the two column blocks, adds bias / residual and writes
+// strided rows (the U-Net concat buffer). With split-K (deep U-Net levels: a handful of row tiles, megabytes of
+// weights) the CTAs of one thread-block cluster hold partial tiles; ranks > 0 park theirs in their own shared memory
+// and rank 0 sums them in rank order over distributed shared memory -- deterministic, no workspace, no atomics.
+// Dropping lo*lo leaves a relative error of ~2^-22 per product, i.e. fp32-grade (the north star's 1e-4 over ~40
+// sequential convolutions rules out plain TF32/fp16).
 #include <algorithm>
 
 #include <cuda_fp16.h>
@@ -25,11 +32,12 @@ namespace sgb {
 constexpr int TC_ROWS = 128;
 constexpr int TC_KC = 32;  // channels per stage
 constexpr int TC_THREADS = 320;  // 8 producer warps + 1 MMA warp + 1 weight-loader warp
+constexpr int BAR_FULL = 0, BAR_FREE = 3, BAR_BFULL = 9;  // per pair stage (<= 3); bars[8] = accumulator done
 
 struct TcArgs {
   const float *in; int in_stride, in_off;
   const int32_t *map; int K, Mout;
-  const float *Wp;  // packed [K][nkc][8 chunks][2 (hi,lo)][N][4]
+  const float *Wp;  // packed fp16 [K][nkc][4 chunks][2 (hi,lo)][N][8 halves]
   int Cin, N, Cout;        // N = Cout rounded up to 16
   int NT;                  // columns per CTA (multiple of 16); gridDim.y = ceil(N / NT)
   const float *in_scale, *in_shift;
@@ -37,8 +45,11 @@ struct TcArgs {
   const float *bias;
   float *out; int out_stride, out_off;
   int nstages, nbstages, tmem_cols, tmem_acols;  // A ring depth (TMEM), weight ring depth (smem), TMEM columns, first A column
+  int ksplit;      // CTAs per cluster along z sharing one tile's iterations (1 = no split)
+  int prefetch;    // pull the packed weights into L2 at kernel start
   int in_packed;   // input rows are already activated + split: per 32-channel chunk [16 words hi pairs | 16 words lo pairs]
   long long *dbg;  // optional timeline buffer (test hook)
+  int skip;        // test hook (timing decomposition only, results are garbage): 1 no tcgen05.st, 2 no MMA, 4 no gather, 8 no weight copy
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,14 +141,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // free[s]: tcgen05.commit, done: accumulator complete.
 __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bars[20];  // [0..3] A full, [4..7] A free, [8] done, [10..14] B full, [15..19] B free
+  __shared__ __align__(8) unsigned long long bars[12];  // [0..2] A full, [3..5] pair free, [8] done, [9..11] weights full
   __shared__ uint32_t s_tmem;
+  __shared__ long long s_dbg[64 * 8];  // in-kernel timeline (test hook): shared memory so that the stamps do not add global stores to the fences
   __shared__ unsigned int s_mask;
   __shared__ int s_list[32];
   __shared__ int s_nact;
   __shared__ __align__(16) float s_scale[512], s_shift[512];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform copy for the role dispatch
+  const bool mark_on = p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+  if (mark_on) p.dbg[64 * 8 + 0] = clock64();
+  if (p.dbg && (p.skip & 32))
+    for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) s_dbg[i] = 0;
   const bool producer = warp < 8;
   const int grp = warp >> 2;          // producer group (0/1)
   const int r = tid & (TC_ROWS - 1);  // row of this producer thread
@@ -151,20 +168,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   const int nt = min(NT, N - n0);                     // columns of this CTA (multiple of 16)
   const uint32_t b_bytes = (uint32_t)NT * TC_KC * 2;  // NT * 64 B (fp16)
   const uint32_t bstage_bytes = 2 * b_bytes;    // weight ring stage: hi + lo
-  const int NS = p.nstages, NSB = p.nbstages;   // NS: A stages in TMEM (64 columns each), NSB: weight stages in smem
+  const int NS = p.nstages;   // A stages in TMEM (32 columns each) == weight stages in shared memory; even
   unsigned char *bring = smem;
-  int32_t *map_s = reinterpret_cast<int32_t *>(bring + (size_t)NSB * bstage_bytes);  // [K][128] (only when p.map)
+  int32_t *map_s = reinterpret_cast<int32_t *>(bring + (size_t)NS * bstage_bytes);  // [K][128] (only when p.map)
 
   if (tid == 0) {
-    for (int i = 0; i < NS; i++) {
-      mbar_init(smem_u32(&bars[i]), TC_ROWS);
-      mbar_init(smem_u32(&bars[4 + i]), 1);
+    for (int i = 0; i < NS / 2; i++) {
+      mbar_init(smem_u32(&bars[BAR_FULL + i]), 8);  // one arrival per producer warp
+      mbar_init(smem_u32(&bars[BAR_FREE + i]), 1);
+      mbar_init(smem_u32(&bars[BAR_BFULL + i]), 1);
     }
     mbar_init(smem_u32(&bars[8]), 1);
-    for (int i = 0; i < NSB; i++) {
-      mbar_init(smem_u32(&bars[10 + i]), 1);
-      mbar_init(smem_u32(&bars[15 + i]), 1);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_mask = 0u;
   }
@@ -178,6 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
+  if (mark_on) p.dbg[64 * 8 + 1] = clock64();
 
   if (has_act) {
     for (int c = tid; c < 512; c += TC_THREADS) {
@@ -189,87 +204,119 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   if (p.map) {
     unsigned int flags = 0u;
     if (producer) {
-      for (int o = grp; o < p.K; o += 2) {
-        int src = row_ok ? __ldg(&p.map[(size_t)o * p.Mout + my_row]) : -1;
-        map_s[o * TC_ROWS + r] = src;
-        if (src >= 0) flags |= 1u << o;
+      // all of this thread's rulebook entries are requested before the first one is used (one memory latency, not K/2)
+      for (int ob = grp; ob < p.K; ob += 28) {
+        int srcv[14];
+#pragma unroll
+        for (int j = 0; j < 14; j++) {
+          const int o = ob + 2 * j;
+          srcv[j] = (o < p.K && row_ok) ? __ldg(&p.map[(size_t)o * p.Mout + my_row]) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 14; j++) {
+          const int o = ob + 2 * j;
+          if (o < p.K) {
+            map_s[o * TC_ROWS + r] = srcv[j];
+            if (srcv[j] >= 0) flags |= 1u << o;
+          }
+        }
       }
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
     if (lane == 0 && flags) atomicOr(&s_mask, flags);
   }
   __syncthreads();
-  if (tid == 0) {
-    int n = 0;
+  if (mark_on) p.dbg[64 * 8 + 2] = clock64();
+  if (tid < 32) {  // compact the active offsets in ascending order
     if (p.map) {
-      unsigned int m = s_mask;
-      for (int o = 0; o < p.K; o++)
-        if (m >> o & 1u) s_list[n++] = o;
-    } else {
-      s_list[n++] = 0;
+      const unsigned int m = s_mask;
+      if (tid < p.K && (m >> tid & 1u)) s_list[__popc(m & ((1u << tid) - 1u))] = tid;
+      if (tid == 0) s_nact = __popc(m);
+    } else if (tid == 0) {
+      s_list[0] = 0;
+      s_nact = 1;
     }
-    s_nact = n;
   }
   __syncthreads();
+  if (mark_on) p.dbg[64 * 8 + 3] = clock64();
   const int nkc = (p.Cin + TC_KC - 1) / TC_KC;
-  const int total = s_nact * nkc;
+  // split-K: the cluster's CTAs take contiguous shares of the tile's (offset, slice) iterations
+  const int S = p.ksplit, z = blockIdx.z;
+  const int total_all = s_nact * nkc;
+  const int i_beg = (int)((long long)total_all * z / S), i_end = (int)((long long)total_all * (z + 1) / S);
+  const int total = i_end - i_beg;
+  const int a0 = i_beg / nkc, k0 = i_beg - a0 * nkc;  // first iteration of this CTA
 
+  // Pipeline unit = a PAIR of consecutive iterations (2P, 2P+1): producer group g fills A stage (ps, g), the loader
+  // brings both weight slices under one transaction barrier, and the MMA thread pays its fixed costs (two barrier
+  // waits, one commit) once per pair and issues up to 8 back-to-back MMAs, which is what lets them pipeline in the
+  // tensor core. Per pair stage ps: full[ps] (8 producer-warp arrivals), bfull[ps] (weights landed),
+  // free[ps] (tcgen05.commit: both the A stages and the weight stages of the pair can be overwritten).
+  const int npairs = (total + 1) >> 1;
+  const int NP = NS >> 1;
   if (producer && p.in_packed) {
     // ---- packed input (activated + split once by sgb_act_split): the gather is pure data movement, so the registers
     //      freed by the missing transform hold TWO future iterations of this thread's row (4 iterations ahead of the
     //      MMA warp counting both groups) -- the L2 latency of the gather is covered without shared memory.
-    float4 va[8], vb[8];
-    int ia = 0, ikc = grp;  // issue cursor: (offset list position, channel slice) of the next own iteration to load
+    uint32_t va[32], vb[32];
+    int ia = a0, ikc = k0 + grp;  // issue cursor: (offset list position, channel slice) of the next own iteration to load
     while (ikc >= nkc) { ikc -= nkc; ia++; }
-    int nload = grp;        // global iteration index of the next load
-    auto load = [&](float4 (&buf)[8]) {
+    int nload = grp;        // CTA-local iteration index of the next load
+    // One gathered row slice = one 128-byte line, every lane a different line: the loads are tag-bound in L1, so the
+    // slice is fetched with four 256-bit loads (LDG.E.256) instead of eight 128-bit ones.
+    auto load = [&](uint32_t (&buf)[32]) {
       if (nload < total) {
         const int o = s_list[ia];
         const int src = p.map ? map_s[o * TC_ROWS + r] : (row_ok ? my_row : -1);
-        if (src >= 0) {
-          const float4 *rp = reinterpret_cast<const float4 *>(p.in + (size_t)src * p.in_stride + p.in_off + ikc * TC_KC);
+        if (src >= 0 && !(p.skip & 4)) {
+          const float *rp = p.in + (size_t)src * p.in_stride + p.in_off + ikc * TC_KC;
 #pragma unroll
-          for (int q = 0; q < 8; q++) buf[q] = __ldg(rp + q);
+          for (int q = 0; q < 4; q++)
+            asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(buf[8 * q + 0]), "=r"(buf[8 * q + 1]), "=r"(buf[8 * q + 2]), "=r"(buf[8 * q + 3]),
+                           "=r"(buf[8 * q + 4]), "=r"(buf[8 * q + 5]), "=r"(buf[8 * q + 6]), "=r"(buf[8 * q + 7])
+                         : "l"(rp + 8 * q));
         } else {
 #pragma unroll
-          for (int q = 0; q < 8; q++) buf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 32; q++) buf[q] = 0u;
         }
       }
       nload += 2;
       ikc += 2;
       while (ikc >= nkc) { ikc -= nkc; ia++; }
     };
-    int s = grp % NS, u = grp / NS;
-    int dbg_i = grp;
-    auto consume = [&](float4 (&buf)[8]) {
-      const bool dbg_on = p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && r == 0 && dbg_i < 64;
-      if (dbg_on) p.dbg[dbg_i * 8 + 0] = clock64();
-      if (u >= 1) mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((u - 1) & 1));
-      if (dbg_on) p.dbg[dbg_i * 8 + 1] = clock64();
-      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
-      uint32_t w[32];
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        w[4 * q + 0] = __float_as_uint(buf[q].x); w[4 * q + 1] = __float_as_uint(buf[q].y);
-        w[4 * q + 2] = __float_as_uint(buf[q].z); w[4 * q + 3] = __float_as_uint(buf[q].w);
+    int ps = 0, u = 0, P = 0;
+    auto consume = [&](uint32_t (&buf)[32]) {
+      const bool work = 2 * P + grp < total;  // an odd tail leaves group 1 without a slice: it only arrives
+      const bool dbg_on = p.dbg && (p.skip & 32) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0 && 2 * P + grp < 64;
+      const int di = 2 * P + grp;
+      if (dbg_on) s_dbg[di * 8 + 0] = clock64();
+      if (u >= 1) mbar_wait(smem_u32(&bars[BAR_FREE + ps]), (uint32_t)((u - 1) & 1));
+      if (dbg_on) s_dbg[di * 8 + 1] = clock64();
+      if (work) {
+        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + (2 * ps + grp) * 32);
+        if (!(p.skip & 1)) tmem_st32(ta, buf);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      tmem_st32(ta, w);
-      const int s_done = s;
-      s += 2;
-      if (s >= NS) { s -= NS; u++; }
-      if (dbg_on) p.dbg[dbg_i * 8 + 2] = clock64();
-      load(buf);  // refill this buffer with own-iteration +2 while the store drains
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      if (dbg_on) p.dbg[dbg_i * 8 + 3] = clock64();
-      mbar_arrive(smem_u32(&bars[s_done]));
-      dbg_i += 2;
+      if (!(p.skip & 16)) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (dbg_on) s_dbg[di * 8 + 2] = clock64();
+      // one arrival per WARP (every lane has completed and fenced its own store): 256 per-thread arrivals on one
+      // mbarrier serialise in the shared-memory atomic unit and were the floor of the whole pipeline
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[BAR_FULL + ps]));
+      // Refill this buffer (own iteration +2) only AFTER the arrive: tcgen05.wait::st / tcgen05.fence compile to
+      // FENCE.VIEW.ASYNC, which also waits for every outstanding global load of the thread -- issued before the
+      // fence, the gather's L2 latency was paid in full on every iteration instead of overlapping the other buffer.
+      if (work) load(buf);
+      if (dbg_on) s_dbg[di * 8 + 3] = clock64();
+      P++;
+      if (++ps == NP) { ps = 0; u++; }
     };
     load(va);
     load(vb);
-    for (int i = grp; i < total; i += 4) {
+    for (int j = 0; j < npairs; j += 2) {
       consume(va);
-      if (i + 2 < total) consume(vb);
+      if (j + 1 < npairs) consume(vb);
     }
   } else if (producer) {
     float4 v[8];
@@ -281,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       const int kvalid = min(TC_KC, p.Cin - c0);
       vsrc = p.map ? map_s[o * TC_ROWS + r] : (row_ok ? my_row : -1);
       const float *rp = (vsrc >= 0) ? p.in + (size_t)vsrc * p.in_stride + p.in_off + c0 : nullptr;
-      const bool fast = (vsrc >= 0) && vec_ok && (kvalid == TC_KC || p.in_packed);
+      const bool fast = (vsrc >= 0) && vec_ok && kvalid == TC_KC;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -295,23 +342,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
         }
       }
     };
-    // iteration i = grp, grp+2, ...: (a_idx, kc) = (i / nkc, i % nkc), stage s = i % NS, use u = i / NS -- all advanced
-    // incrementally (no integer division in the loop)
+    // own iterations i = grp, grp+2, ... = slot grp of pair P; (a_idx, kc) advanced incrementally
     int i = grp;
-    int kc = grp, a_idx = 0;
+    int kc = k0 + grp, a_idx = a0;
     while (kc >= nkc) { kc -= nkc; a_idx++; }
-    int s = grp % NS, u = grp / NS;
+    int ps = 0, u = 0;
     if (i < total) load_iter(a_idx, kc);
-    for (; i < total; i += 2) {
-      const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && r == 0 && i < 64;
-      if (dbg_on) p.dbg[i * 8 + 0] = clock64();
-      if (u >= 1) mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((u - 1) & 1));
-      if (dbg_on) p.dbg[i * 8 + 1] = clock64();
-      const int c0 = kc * TC_KC;
-      const int kvalid = min(TC_KC, p.Cin - c0);
-      // ---- A: registers -> (BN+ReLU) -> hi / lo -> tensor memory (lane = row, column = channel) -----------
-      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + s * 32);
-      {
+    for (int P = 0; P < npairs; P++, i += 2) {
+      const bool work = i < total;
+      if (u >= 1) mbar_wait(smem_u32(&bars[BAR_FREE + ps]), (uint32_t)((u - 1) & 1));
+      if (work) {
+        const int c0 = kc * TC_KC;
+        const int kvalid = min(TC_KC, p.Cin - c0);
+        // ---- A: registers -> (BN+ReLU) -> hi / lo -> tensor memory (lane = row, column = channel) -----------
+        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + (2 * ps + grp) * 32);
         // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): |x - hi - lo| <= 2^-22 |x| (or 2^-25 absolute when lo is
         // subnormal); two halves per 32-bit TMEM column (channel 2c in the low half). 16 columns hi + 16 columns lo.
         uint32_t hv[16], lv[16];
@@ -342,101 +386,183 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
         }
         tmem_st16(ta, hv);
         tmem_st16(ta + 16u, lv);
+        kc += 2;
+        while (kc >= nkc) { kc -= nkc; a_idx++; }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      const int s_done = s;
-      kc += 2;
-      while (kc >= nkc) { kc -= nkc; a_idx++; }
-      s += 2;
-      if (s >= NS) { s -= NS; u++; }
-      if (dbg_on) p.dbg[i * 8 + 2] = clock64();
-      if (i + 2 < total) load_iter(a_idx, kc);  // next gather of this group is in flight during the waits below
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      if (dbg_on) p.dbg[i * 8 + 3] = clock64();
-      mbar_arrive(smem_u32(&bars[s_done]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[BAR_FULL + ps]));
+      if (work && i + 2 < total) load_iter(a_idx, kc);  // after the fence (it would wait for these loads), see above
+      if (++ps == NP) { ps = 0; u++; }
     }
   } else if (warp == 9) {
     // ---- weight loader: one elected lane streams the packed slices with TMA bulk copies (cp.async.bulk, async proxy:
-    //      no generic->async fence needed) into a deeper ring; completion is signalled on the stage's mbarrier by
-    //      complete_tx. Global layout [chunk q][hi|lo][N][16 B] == shared layout [q][hi nt | lo nt][16 B] when the CTA
-    //      owns all N columns, so a whole slice is ONE bulk copy; with a column split it is one copy per (q, part).
-    {
-      int sb = 0, ub = 0, kc = 0, a_idx = 0;
-      for (int i = 0; i < total; i++) {
-        if (ub >= 1) mbar_wait(smem_u32(&bars[15 + sb]), (uint32_t)((ub - 1) & 1));
-        const int o = s_list[a_idx];
-        const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
-        const int ksteps = (kvalid + 15) >> 4;  // K = 16 halves per tcgen05.mma
-        const float4 *g = reinterpret_cast<const float4 *>(p.Wp) + ((size_t)o * nkc + kc) * (size_t)N * 8;
-        const uint32_t bb = smem_u32(bring + (size_t)sb * bstage_bytes);
-        const uint32_t bar = smem_u32(&bars[10 + sb]);
-        const int nseg = 4 * ksteps;  // (chunk, part) segments of nt*16 bytes
-        const uint32_t bytes = (uint32_t)nseg * (uint32_t)nt * 16u;
-        if (lane == 0)
-          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-        __syncwarp();
-        if (nt == N) {
-          if (lane == 0)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(bb), "l"(g), "r"(bytes), "r"(bar) : "memory");
-        } else if (lane < nseg) {  // column split: one bulk copy per (chunk, part) segment, one lane each
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(bb + (uint32_t)(lane * nt) * 16u), "l"(g + (size_t)lane * N + n0), "r"((uint32_t)nt * 16u), "r"(bar)
-                       : "memory");
+    //      no generic->async fence needed); completion is signalled on the pair's mbarrier by complete_tx. Global
+    //      layout [chunk q][hi|lo][N][16 B] == shared layout [q][hi nt | lo nt][16 B] when the CTA owns all N columns,
+    //      so a whole slice is ONE bulk copy; with a column split it is one copy per (q, part), one lane each.
+    if (p.prefetch) {
+      // every CTA streams the weights in the same order, so without this they are cold for everybody at once
+      const long long wbytes = (long long)p.K * nkc * N * 128;
+      const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      const int ncta = min((int)(gridDim.x * gridDim.y * gridDim.z), 256);
+      if (lin < ncta) {
+        const char *wb = reinterpret_cast<const char *>(p.Wp);
+        for (long long off = ((long long)lin * 32 + lane) * 4096; off < wbytes; off += (long long)ncta * 32 * 4096) {
+          const uint32_t sz = (uint32_t)min(4096ll, wbytes - off);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wb + off), "r"(sz) : "memory");
         }
-        if (++sb == NSB) { sb = 0; ub++; }
-        if (++kc == nkc) { kc = 0; a_idx++; }
       }
     }
-  } else if (warp == 8 && lane == 0) {
-    // ---- MMA issuer: per 8-channel k-step two instructions
+    int ps = 0, ub = 0, kc = k0, a_idx = a0;
+    for (int P = 0; P < npairs; P++) {
+      if (ub >= 1) mbar_wait(smem_u32(&bars[BAR_FREE + ps]), (uint32_t)((ub - 1) & 1));
+      const int nit = min(2, total - 2 * P);
+      const uint32_t bar = smem_u32(&bars[BAR_BFULL + ps]);
+      // slot 0 / slot 1 of the pair: offset, slice, 16-channel k-steps
+      const int o0 = s_list[a_idx], kc0 = kc;
+      int kc1 = kc + 1, a1 = a_idx;
+      if (kc1 == nkc) { kc1 = 0; a1++; }
+      const int o1 = (nit > 1) ? s_list[a1] : 0;
+      const int ks0 = (min(TC_KC, p.Cin - kc0 * TC_KC) + 15) >> 4;
+      const int ks1 = (nit > 1) ? (min(TC_KC, p.Cin - kc1 * TC_KC) + 15) >> 4 : 0;
+      const int nseg0 = 4 * ks0, nseg1 = 4 * ks1;  // (chunk, part) segments of nt*16 bytes
+      if (p.skip & 8) {
+        if (lane == 0) mbar_arrive(bar);
+        if (++ps == NP) { ps = 0; ub++; }
+        kc += 2;
+        while (kc >= nkc) { kc -= nkc; a_idx++; }
+        continue;
+      }
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)(nseg0 + nseg1) * (uint32_t)nt * 16u;
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+      }
+      __syncwarp();
+      const float4 *g0 = reinterpret_cast<const float4 *>(p.Wp) + ((size_t)o0 * nkc + kc0) * (size_t)N * 8;
+      const float4 *g1 = reinterpret_cast<const float4 *>(p.Wp) + ((size_t)o1 * nkc + kc1) * (size_t)N * 8;
+      const uint32_t bb0 = smem_u32(bring + (size_t)(2 * ps) * bstage_bytes), bb1 = bb0 + bstage_bytes;
+      if (nt == N) {
+        if (lane == 0)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(bb0), "l"(g0), "r"((uint32_t)nseg0 * (uint32_t)nt * 16u), "r"(bar) : "memory");
+        if (lane == 1 && nit > 1)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(bb1), "l"(g1), "r"((uint32_t)nseg1 * (uint32_t)nt * 16u), "r"(bar) : "memory");
+      } else if (lane < nseg0 + nseg1) {  // column split: one bulk copy per (chunk, part) segment
+        const bool second = lane >= nseg0;
+        const int sg = second ? lane - nseg0 : lane;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((second ? bb1 : bb0) + (uint32_t)(sg * nt) * 16u), "l"((second ? g1 : g0) + (size_t)sg * N + n0),
+                     "r"((uint32_t)nt * 16u), "r"(bar)
+                     : "memory");
+      }
+      if (++ps == NP) { ps = 0; ub++; }
+      kc += 2;
+      while (kc >= nkc) { kc -= nkc; a_idx++; }
+    }
+  } else if (warp_u == 8) {
+    // ---- MMA issuer: per 16-channel k-step two instructions
     //        D[:, 0:2nt]  += A_hi * [B_hi | B_lo]     (N = 2nt)
     //        D[:, nt:2nt] += A_lo *  B_hi             (N = nt)
     //      so columns [0,nt) hold hi*hi and [nt,2nt) the two correction products (summed in the epilogue).
-    //      Descriptors are advanced by adding constants to their low word; the issue loop is kept minimal because
-    //      a single thread's instruction stream paces the tensor pipe (measured ~50 cycles / tcgen05.mma at N<=64).
+    //      The WHOLE warp runs this loop and one elected lane issues: with warp-uniform control flow and operands the
+    //      compiler keeps descriptors in uniform registers and emits bare UTCHMMA; issued from a divergent
+    //      `lane == 0` branch every instruction was wrapped in an R2UR + VOTEU/ELECT/BRA.U.ANY waterfall loop, and that
+    //      single thread's instruction stream (not the tensor pipe) paced the whole kernel.
     // instruction descriptor: D = f32 (1 << 4), A = B = f16 (format 0), both K-major, N >> 3, M >> 4
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const int total_u = __shfl_sync(0xffffffffu, total, 0);
+    const int npairs_u = (total_u + 1) >> 1;
+    const int k0_u = __shfl_sync(0xffffffffu, k0, 0);
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * nt) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
     const uint32_t idesc1 = (1u << 4) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
     const uint32_t b_lbo = (uint32_t)(2 * nt) * 16;
     const uint64_t b_step = (uint64_t)((2 * b_lbo) >> 4);
+    const uint32_t bring_u = smem_u32(bring);
+    const uint32_t bars_u = smem_u32(&bars[0]);
+    const uint32_t acol0 = tmem_u + (uint32_t)p.tmem_acols;
     uint32_t first = 0u;  // 0 for the very first MMA (overwrite), then 1
-    int s = 0, sb = 0, kc = 0;
-    uint32_t pa = 0u, pb = 0u;
-    for (int i = 0; i < total; i++) {
-      const bool dbg_on = p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && i < 64;
-      if (dbg_on) p.dbg[i * 8 + 4] = clock64();
-      mbar_wait(smem_u32(&bars[10 + sb]), pb);
-      if (dbg_on) p.dbg[i * 8 + 5] = clock64();
-      mbar_wait(smem_u32(&bars[s]), pa);
-      if (dbg_on) p.dbg[i * 8 + 6] = clock64();
+    int ps = 0, kc = k0_u;
+    uint32_t par = 0u;
+    for (int P = 0; P < npairs_u; P++) {
+      const bool dbg_on = p.dbg && (p.skip & 32) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && P < 64 && leader;
+      if (dbg_on) s_dbg[P * 8 + 4] = clock64();
+      mbar_wait(bars_u + 8u * (uint32_t)(BAR_BFULL + ps), par);
+      if (dbg_on) s_dbg[P * 8 + 5] = clock64();
+      mbar_wait(bars_u + 8u * (uint32_t)(BAR_FULL + ps), par);
+      if (dbg_on) s_dbg[P * 8 + 6] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
-      const int ksteps = (kvalid + 15) >> 4;
-      const uint32_t sbt = smem_u32(bring + (size_t)sb * bstage_bytes);
-      uint64_t dbb = umma_desc(sbt, b_lbo, 128);
-      uint32_t ah = tmem + (uint32_t)(p.tmem_acols + s * 32), al = ah + 16u;
-      for (int ks = 0; ks < ksteps; ks++) {
-        umma_tf32_ts(tmem, ah, dbb, idesc2, (ks == 0) ? first : 1u);
-        umma_tf32_ts(tmem + (uint32_t)nt, al, dbb, idesc1, 1u);
-        ah += 8u; al += 8u; dbb += b_step;
+      const int nit = min(2, total_u - 2 * P);
+      for (int h = 0; h < nit; h++) {
+        const int kvalid = min(TC_KC, p.Cin - kc * TC_KC);
+        const int ksteps = (kvalid + 15) >> 4;
+        const uint32_t sbt = bring_u + (uint32_t)(2 * ps + h) * bstage_bytes;
+        uint64_t dbb = umma_desc(sbt, b_lbo, 128);
+        uint32_t ah = acol0 + (uint32_t)((2 * ps + h) * 32), al = ah + 16u;
+        for (int ks = 0; ks < ksteps; ks++) {
+          if (leader && !(p.skip & 2)) {
+            umma_tf32_ts(tmem_u, ah, dbb, idesc2, first);
+            umma_tf32_ts(tmem_u + (uint32_t)nt, al, dbb, idesc1, 1u);
+          }
+          first = 1u;
+          ah += 8u; al += 8u; dbb += b_step;
+        }
+        if (++kc == nkc) kc = 0;
       }
-      first = 1u;
-      umma_commit(smem_u32(&bars[4 + s]));    // frees the A stage once the MMAs above have read it
-      umma_commit(smem_u32(&bars[15 + sb]));  // ... and the weight stage
-      if (dbg_on) p.dbg[i * 8 + 7] = clock64();
-      if (++s == NS) { s = 0; pa ^= 1u; }
-      if (++sb == NSB) { sb = 0; pb ^= 1u; }
-      if (++kc == nkc) kc = 0;
+      if (leader) umma_commit(bars_u + 8u * (uint32_t)(BAR_FREE + ps));  // frees both A stages and both weight stages of the pair
+      __syncwarp();
+      if (dbg_on) s_dbg[P * 8 + 7] = clock64();
+      if (++ps == NP) { ps = 0; par ^= 1u; }
     }
-    if (total > 0) umma_commit(smem_u32(&bars[8]));
+    if (leader && total_u > 0) umma_commit(bars_u + 8u * 8u);
+    __syncwarp();
   }
   // ---- epilogue: TMEM lane = output row; warp w reads lanes 32*(w%4).., column half w/4 -----------------
-  if (producer) {
+  const bool split = S > 1;
+  if (mark_on) p.dbg[64 * 8 + 4] = clock64();
+  const uint32_t pbuf = smem_u32(bring);  // split-K partial tile [nt columns][128 rows] f32 (the weight ring is idle by now)
+  if (split) {
+    if (producer && z > 0) {
+      if (total > 0) {
+        mbar_wait(smem_u32(&bars[8]), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const int lane_grp = warp & 3, chalf = warp >> 2;
+      const int cbeg = chalf * (nt >> 1), cend = cbeg + (nt >> 1);
+      for (int cb = cbeg; cb < cend; cb += 8) {
+        uint32_t v[8], c[8];
+        if (total > 0) {
+          uint32_t taddr = tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cb;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(taddr));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+                       : "r"(taddr + (uint32_t)nt));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++) v[e] = c[e] = 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const float x = __uint_as_float(v[e]) + __uint_as_float(c[e]);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(pbuf + (uint32_t)(((cb + e) * TC_ROWS + lane_grp * 32 + lane) * 4)), "f"(x) : "memory");
+        }
+      }
+    }
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (producer && (!split || z == 0)) {
     if (total > 0) {
       mbar_wait(smem_u32(&bars[8]), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    if (mark_on) p.dbg[64 * 8 + 5] = clock64();
     const int lane_grp = warp & 3, chalf = warp >> 2;
     const int row = row0 + lane_grp * 32 + lane;
     const int cbeg = chalf * (nt >> 1), cend = cbeg + (nt >> 1);
@@ -456,6 +582,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       } else {
 #pragma unroll
         for (int e = 0; e < 8; e++) v[e] = 0u;
+      }
+      if (split) {  // add the other ranks' partial tiles in rank order (distributed shared memory)
+        for (int zz = 1; zz < S; zz++) {
+          uint32_t rbase;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbase) : "r"(pbuf), "r"(zz));
+          float t[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(t[e]) : "r"(rbase + (uint32_t)(((cb + e) * TC_ROWS + lane_grp * 32 + lane) * 4)) : "memory");
+#pragma unroll
+          for (int e = 0; e < 8; e++) v[e] = __float_as_uint(__uint_as_float(v[e]) + t[e]);
+        }
       }
       if (row < p.Mout) {
         const int col = n0 + cb;
@@ -492,11 +630,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       }
     }
   }
+  if (split) {  // ranks > 0 keep their shared memory alive until rank 0 has read it
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (mark_on) p.dbg[64 * 8 + 6] = clock64();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+  if (mark_on) p.dbg[64 * 8 + 7] = clock64();
+  if (mark_on && (p.skip & 32))
+    for (int i = 0; i < 64 * 8; i++) p.dbg[i] = s_dbg[i];
 }
 
 }  // namespace sgb
@@ -533,10 +679,18 @@ __global__ void act_split_kernel(const float *__restrict__ x, int x_stride, int 
 }  // namespace sgb
 
 static long long *g_tc_dbg = nullptr;
+static int g_tc_prefetch = 0, g_tc_maxb = 3, g_tc_maxsplit = 8, g_tc_skip = 0;
 
 extern "C" {
 
 void sgb_test_set_tc_debug(long long *d_buf) { g_tc_dbg = d_buf; }
+void sgb_test_set_tc_skip(int mask) { g_tc_skip = mask; }
+// test/bench hook: weight prefetch on/off, most pair stages in the ring (1..3), largest split-K cluster (1 = off)
+void sgb_test_set_tc_tuning(int prefetch, int max_pairs, int max_ksplit) {
+  g_tc_prefetch = prefetch;
+  g_tc_maxb = std::max(1, std::min(max_pairs, 3));
+  g_tc_maxsplit = std::max(1, std::min(max_ksplit, 8));
+}
 
 int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
                   float *d_y, int M, int C, void *stream) {
@@ -580,6 +734,7 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   p.bias = d_bias;
   p.out = d_out; p.out_stride = out_stride; p.out_off = out_off;
   p.dbg = g_tc_dbg;
+  p.skip = g_tc_skip;
   p.in_packed = in_packed;
   // Column split: few row tiles (deep U-Net levels) would leave most SMs idle and make one CTA stream all the
   // weights, so N is cut into NT-column CTAs until the grid covers the machine (NT multiple of 16, >= 32).
@@ -594,24 +749,55 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   p.NT = NT;
   size_t bstage = 2 * (size_t)NT * TC_KC * 2;      // weight ring stage (fp16 hi + lo) in shared memory
   size_t map_bytes = d_map ? (size_t)K * TC_ROWS * 4 : 0;
-  // TMEM budget: accumulator [main | corrections] = 2*NT columns, then the A ring (64 columns per stage: hi + lo).
-  // 256 columns (two CTAs per SM) when that leaves >= 2 A stages, else all 512.
+  // TMEM budget: accumulator [main | corrections] = 2*NT columns, then the A ring (32 columns per stage: hi + lo pairs;
+  // an even number of stages because the pipeline moves in pairs). 256 columns (two CTAs per SM) when that leaves
+  // >= 4 stages (two pairs, so gathers overlap the MMAs), else all 512. The weight ring in shared memory has the same number of stages.
   int dcols = 2 * NT;
   int acols0 = (dcols + 31) / 32 * 32;
-  if (acols0 + 2 * 32 <= 256) { p.tmem_cols = 256; p.nstages = (256 - acols0) / 32; }
-  else { p.tmem_cols = 512; p.nstages = (512 - acols0) / 32; }
-  p.nstages = std::min(p.nstages, 4);
+  int ns = ((256 - acols0) / 32) & ~1;
+  if (ns >= 4) { p.tmem_cols = 256; }
+  else { p.tmem_cols = 512; ns = ((512 - acols0) / 32) & ~1; }
+  ns = std::min(ns, std::min(6, 2 * g_tc_maxb));
+  const size_t ring_cap = (p.tmem_cols == 256) ? 64 * 1024 : 100 * 1024;  // one CTA per SM when it owns all of TMEM
+  while (ns > 2 && (size_t)ns * bstage > ring_cap) ns -= 2;
+  p.nstages = ns;
+  p.nbstages = ns;
   p.tmem_acols = acols0;
-  p.nbstages = (int)std::max<size_t>(2, std::min<size_t>(4, (96 * 1024 - map_bytes) / bstage));
+  p.prefetch = g_tc_prefetch;
+  // split-K: when even the narrowest column split leaves most SMs idle, a cluster of S CTAs shares each tile's
+  // iterations (S <= 8, the portable cluster size) and reduces through distributed shared memory.
+  const int nkc = (Cin + TC_KC - 1) / TC_KC;
+  int ctas = tiles * div_up(N, NT), S = 1;
+  if (ctas * 2 <= kNumSMs && p.tmem_cols == 256 && (size_t)p.nbstages * bstage >= (size_t)NT * TC_ROWS * 4) {
+    S = std::min({g_tc_maxsplit, 2 * kNumSMs / ctas, std::max(1, K * nkc / 4)});
+    S = std::max(S, 1);
+  }
+  p.ksplit = S;
   size_t smem = bstage * p.nbstages + map_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
     SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  dim3 grid(tiles, div_up(N, NT));
-  spconv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  dim3 grid(tiles, div_up(N, NT), S);
+  if (S == 1) {
+    spconv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = S;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SGB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spconv_tc_kernel, p));
+  }
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
@@ -645,7 +831,26 @@ __global__ void umma_rate_kernel(int N, int reps, int per_commit, long long *out
     long long t0 = clock64();
     uint32_t phase = 0;
     for (int r = 0; r < reps; r += per_commit) {
-      if (a_in_tmem > 0) {
+      if (a_in_tmem >= 100) {
+        // kind::f16 issue patterns of the conv kernel, nt = N: 100 = [N=2nt at D | N=nt at D+nt] (overlapping accumulators),
+        // 101 = three N=nt products into ONE accumulator, 102 = [N=2nt at D | N=nt at a disjoint accumulator]
+        const uint32_t i1 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+        const uint32_t i2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | (8u << 24);
+        for (int k = 0; k < per_commit; k++) {
+          const uint32_t ta = tmem + 384 + 8 * (k & 7);
+          if (a_in_tmem == 100) {
+            umma_tf32_ts(tmem, ta, db, i2, 1u);
+            umma_tf32_ts(tmem + N, ta + 16, db, i1, 1u);
+          } else if (a_in_tmem == 101) {
+            umma_tf32_ts(tmem, ta, db, i1, 1u);
+            umma_tf32_ts(tmem, ta + 16, db, i1, 1u);
+            umma_tf32_ts(tmem, ta, db, i1, 1u);
+          } else {
+            umma_tf32_ts(tmem, ta, db, i2, 1u);
+            umma_tf32_ts(tmem + 256, ta + 16, db, i1, 1u);
+          }
+        }
+      } else if (a_in_tmem > 0) {
         for (int k = 0; k < per_commit; k++) umma_tf32_ts(tmem + 64 * (k % a_in_tmem), tmem + 256 + 8 * (k & 7), db, idesc, 1u);
       } else {
         for (int k = 0; k < per_commit; k++) umma_tf32(tmem + 64 * (k % (-a_in_tmem + 1)), da, db, idesc, 1u);

@@ -27,6 +27,41 @@ from ..util import cuda_cast, force_fp32, rle_encode_ids
 from .blocks import MLP, ResidualBlock, UBlock
 
 
+class _HostFetcher(object):
+    """Device -> host reads of result arrays without stalling the forward: every tensor is copied into pinned memory
+    on a side stream as soon as it is final; `finish()` waits once and hands out numpy arrays that own their pinned
+    block (torch's caching host allocator recycles it when the array dies)."""
+    _streams = {}
+
+    def __init__(self, device):
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        if key not in _HostFetcher._streams:
+            _HostFetcher._streams[key] = torch.cuda.Stream(device=key)
+        self.stream = _HostFetcher._streams[key]
+        self.items = []
+
+    def add(self, name, t):
+        if t is None:
+            self.items.append((name, None))
+            return
+        if not t.is_cuda:
+            self.items.append((name, t))
+            return
+        t = t.contiguous()
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+        t.record_stream(self.stream)
+        self.items.append((name, h))
+
+    def finish(self):
+        self.stream.synchronize()
+        return {k: (h.numpy() if h is not None else None) for k, h in self.items}
+
+
 class SoftGroup(nn.Module):
 
     def __init__(self,
@@ -162,14 +197,19 @@ class SoftGroup(nn.Module):
                 pt_offset_labels = self.merge_4_parts(pt_offset_labels)
         semantic_preds = semantic_scores.max(1)[1]
         ret = dict(scan_id=scan_ids[0] if scan_ids else None)
+        # the reference reads these back with blocking .cpu() calls in the middle of the forward (softgroup.py:317-331);
+        # here the copies go to pinned memory on a side stream and are awaited once, after the instance branch
+        fetch = _HostFetcher(semantic_scores.device) if not device_only else None
         if not device_only:
             if 'semantic' in eval_tasks or 'panoptic' in eval_tasks:
-                ret.update(dict(semantic_labels=semantic_labels.cpu().numpy(),
-                                instance_labels=instance_labels.cpu().numpy()))
+                fetch.add('semantic_labels', semantic_labels)
+                fetch.add('instance_labels', instance_labels)
             if 'semantic' in eval_tasks:
-                ret.update(dict(coords_float=coords_float.cpu().numpy(), color_feats=color_feats.cpu().numpy(),
-                                semantic_preds=semantic_preds.cpu().numpy(), offset_preds=pt_offsets.cpu().numpy(),
-                                offset_labels=pt_offset_labels.cpu().numpy()))
+                fetch.add('coords_float', coords_float)
+                fetch.add('color_feats', color_feats)
+                fetch.add('semantic_preds', semantic_preds)
+                fetch.add('offset_preds', pt_offsets)
+                fetch.add('offset_labels', pt_offset_labels)
         if not self.semantic_only and ('instance' in eval_tasks or 'panoptic' in eval_tasks):
             proposals_idx, proposals_offset = self.forward_grouping(semantic_scores, pt_offsets, batch_idxs,
                                                                     coords_float, self.grouping_cfg)
@@ -192,6 +232,8 @@ class SoftGroup(nn.Module):
                     ret.update(panoptic_preds=self.panoptic_fusion(semantic_preds.cpu().numpy(), inst))
         if device_only:
             ret.update(semantic_preds=semantic_preds, pt_offsets=pt_offsets)
+        else:
+            ret.update(fetch.finish())
         if self.profile_stages:
             torch.cuda.synchronize()
             self.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._events[:-1], self._events[1:])}

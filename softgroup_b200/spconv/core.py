@@ -24,7 +24,11 @@ from ..ops._lib import check, ptr
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of torch's current stream; the C entry point avoids ~10 us of Python per launch
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except Exception:  # older torch: public (slower) path
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 class SparseConvTensor(object):
