@@ -198,12 +198,16 @@ int sgb_spconv_forward(const float *d_in, int in_stride, int in_off, const int32
                        const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
                        int out_stride, int out_off, void *stream);
 
-/* Tensor-core version of sgb_spconv_forward (tcgen05.mma kind::tf32 with TMEM accumulators; 3xTF32 error-compensated
- * split so results are fp32-grade). Same semantics; weights come pre-split and pre-packed in ONE array:
- *   N = Cout rounded up to 16 (<= 256), nkc = ceil(Cin/32), Cin <= 256;
- *   Wp f32 [K][nkc][8][2][N][4]: element (k, kc, q, part, n, e) = part(W[k][32*kc + 4*q + e][n]) (0 outside Cin/Cout),
- *   part 0 = hi = W with the low 13 mantissa bits cleared (TF32-exact), part 1 = lo = W - hi.
- * sgb_spconv_tc_packed_floats returns the length of the packed array. */
+/* Tensor-core version of sgb_spconv_forward (tcgen05.mma kind::f16, fp32 accumulators in TMEM). Every operand value x
+ * is carried as two fp16 numbers hi = fp16(x), lo = fp16(x - hi) and the product is hi*hi + hi*lo + lo*hi, so results
+ * are fp32-grade. Same semantics as sgb_spconv_forward; Cin <= 512, Cout <= 256. Weights come
+ * pre-split and pre-packed in ONE array (softgroup_b200/spconv/core.py:pack_weight_tc):
+ *   N = Cout rounded up to 16, nkc = ceil(Cin/32);
+ *   Wp fp16 [K][nkc][4][2][N][8]: element (k, kc, q, part, n, e) = part(W[k][32*kc + 8*q + e][n]) (0 outside Cin/Cout),
+ *   part 0 = hi, part 1 = lo -- i.e. per (k, kc) a UMMA K-major / no-swizzle operand [B_hi | B_lo] of 16-byte chunks.
+ *   The array is passed as float* (two halves per 32-bit word); sgb_spconv_tc_packed_floats returns its length in words.
+ * in_packed != 0: d_in holds rows already activated and split by sgb_act_split (d_in_scale/d_in_shift must be NULL,
+ * in_stride and in_off multiples of 32 words). */
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout);
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
                           const float *d_Wp, int Cin, int Cout, const float *d_in_scale, const float *d_in_shift,
