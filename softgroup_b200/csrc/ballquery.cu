@@ -4,10 +4,15 @@
 //   (1) cell hash:   cell = floor(p / h), h = radius*(1+1e-4) in fp64; 64-bit key (segment, cx, cy, cz) ->
 //                    open-addressing hash (atomicCAS); counts per cell; exclusive scan; scatter of
 //                    (x,y,z,idx) records so every cell is one contiguous run of 16-byte records;
-//   (2) query:       one CTA per occupied cell. The <=27 neighbouring runs are staged in shared memory
-//                    and bitonic-sorted by point index ONCE per cell; each query of the cell (one warp) then
-//                    streams the staged candidates in index order -> ballot/popc compaction gives the
-//                    ascending list directly and the "first 1000 by index" cap (:43-48) is a loop exit.
+//   (2) query:       a persistent grid (one 1024-thread CTA per SM) pulls work items = (occupied cell, chunk of
+//                    <= 128 queries of that cell). The <= 27 neighbouring runs are staged in shared memory and put
+//                    in ascending point-index order in LINEAR time: a bitmap over the stencil's id range plus
+//                    per-word prefix popcounts gives every record its rank (bitonic sort only when the id range
+//                    does not fit the bitmap). Each query (one warp) then streams the staged candidates in index
+//                    order in two passes: count (the ballot masks are kept in shared memory), one atomicAdd on
+//                    the global cursor like the reference (:52), then a coalesced write of the hits -- the
+//                    "first 1000 by index" cap (:43-48) is a loop exit. Stencils larger than the staging area
+//                    fall back to an exact index-order scan of the whole segment.
 // Exactness: the distance is evaluated with the reference's compiled contraction order
 //   d2 = fma(dz,dz, fma(dx,dx, dy*dy)),  hit iff d2 < radius*radius   (strict, fp32)
 // and any pair with d2 < r^2 differs by < h in every coordinate, so it lies in the 27-cell stencil.

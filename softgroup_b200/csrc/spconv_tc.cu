@@ -81,7 +81,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -113,32 +113,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // upper half <- first source
   return *reinterpret_cast<__half2 *>(&r);
 }
-__device__ __forceinline__ float4 tf32_hi(float4 v) {
-  float4 h;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-  return h;
-}
-
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
-// Warp roles: warps 0-3 = producer group 0, warps 4-7 = producer group 1 (one output row per thread; the groups
-// take alternate pipeline iterations), warp 8 = MMA issuer (one elected lane). Producers keep the NEXT iteration's
-// gathered row slice in registers while the current one is being split and stored, so the L2 latency of the gather
-// overlaps the stores, the weight copy (cp.async) and the other group's work. full[s]: 128 producer arrivals,
-// free[s]: tcgen05.commit, done: accumulator complete.
+// Warp roles: warps 0-3 = producer group 0, warps 4-7 = producer group 1 (one output row per thread; group g fills slot g
+// of every iteration pair), warp 8 = MMA issuer (warp-uniform, one elected lane), warp 9 = weight loader (TMA bulk copies).
+// Barriers per pair stage: full (8 producer-warp arrivals), bfull (weights: expect_tx), free (tcgen05.commit);
+// bars[8]: accumulator complete.
 __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bars[12];  // [0..2] A full, [3..5] pair free, [8] done, [9..11] weights full
@@ -504,8 +491,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
         uint32_t ah = acol0 + (uint32_t)((2 * ps + h) * 32), al = ah + 16u;
         for (int ks = 0; ks < ksteps; ks++) {
           if (leader && !(p.skip & 2)) {
-            umma_tf32_ts(tmem_u, ah, dbb, idesc2, first);
-            umma_tf32_ts(tmem_u + (uint32_t)nt, al, dbb, idesc1, 1u);
+            umma_f16_ts(tmem_u, ah, dbb, idesc2, first);
+            umma_f16_ts(tmem_u + (uint32_t)nt, al, dbb, idesc1, 1u);
           }
           first = 1u;
           ah += 8u; al += 8u; dbb += b_step;
@@ -839,19 +826,19 @@ __global__ void umma_rate_kernel(int N, int reps, int per_commit, long long *out
         for (int k = 0; k < per_commit; k++) {
           const uint32_t ta = tmem + 384 + 8 * (k & 7);
           if (a_in_tmem == 100) {
-            umma_tf32_ts(tmem, ta, db, i2, 1u);
-            umma_tf32_ts(tmem + N, ta + 16, db, i1, 1u);
+            umma_f16_ts(tmem, ta, db, i2, 1u);
+            umma_f16_ts(tmem + N, ta + 16, db, i1, 1u);
           } else if (a_in_tmem == 101) {
-            umma_tf32_ts(tmem, ta, db, i1, 1u);
-            umma_tf32_ts(tmem, ta + 16, db, i1, 1u);
-            umma_tf32_ts(tmem, ta, db, i1, 1u);
+            umma_f16_ts(tmem, ta, db, i1, 1u);
+            umma_f16_ts(tmem, ta + 16, db, i1, 1u);
+            umma_f16_ts(tmem, ta, db, i1, 1u);
           } else {
-            umma_tf32_ts(tmem, ta, db, i2, 1u);
-            umma_tf32_ts(tmem + 256, ta + 16, db, i1, 1u);
+            umma_f16_ts(tmem, ta, db, i2, 1u);
+            umma_f16_ts(tmem + 256, ta + 16, db, i1, 1u);
           }
         }
       } else if (a_in_tmem > 0) {
-        for (int k = 0; k < per_commit; k++) umma_tf32_ts(tmem + 64 * (k % a_in_tmem), tmem + 256 + 8 * (k & 7), db, idesc, 1u);
+        for (int k = 0; k < per_commit; k++) umma_f16_ts(tmem + 64 * (k % a_in_tmem), tmem + 256 + 8 * (k & 7), db, idesc, 1u);
       } else {
         for (int k = 0; k < per_commit; k++) umma_tf32(tmem + 64 * (k % (-a_in_tmem + 1)), da, db, idesc, 1u);
       }
