@@ -27,6 +27,25 @@ from ..util import cuda_cast, force_fp32, rle_encode_ids
 from .blocks import MLP, ResidualBlock, UBlock
 
 
+def expand_voxel_entries(proposals_idx, v2p_map, num_voxels):
+    """(proposal, voxel) entries -> (proposal, point) entries for every point of the voxel (lvl_fusion, the sparse
+    counterpart of `mask_pred[:, v2p_map.long()]`, softgroup.py:560-561). v2p_map: int [N] voxel of every point.
+    Returns (int32 [S, 2] entries in entry order, points of one voxel ascending; int64 [S] source entry of each row)."""
+    dev = proposals_idx.device
+    v2p = v2p_map.long()
+    cnt = torch.bincount(v2p, minlength=num_voxels)  # points per voxel
+    start = torch.cumsum(cnt, 0) - cnt
+    pts_by_voxel = torch.argsort(v2p, stable=True)  # points grouped by voxel, ascending inside a voxel
+    vox = proposals_idx[:, 1].long()
+    rep = cnt[vox]
+    row_of = torch.repeat_interleave(torch.arange(vox.numel(), device=dev), rep)
+    first = torch.cumsum(rep, 0) - rep  # first output row of every entry
+    within = torch.arange(row_of.numel(), device=dev) - first[row_of]
+    pts = pts_by_voxel[start[vox[row_of]] + within]
+    out = torch.stack([proposals_idx[row_of, 0].long(), pts], 1).int().contiguous()
+    return out, row_of
+
+
 class _HostFetcher(object):
     """Device -> host reads of result arrays without stalling the forward: every tensor is copied into pinned memory
     on a side stream as soon as it is final; `finish()` waits once and hands out numpy arrays that own their pinned
@@ -175,9 +194,11 @@ class SoftGroup(nn.Module):
         voxel_feats = voxelization(feats.contiguous(), p2v_map.contiguous())
         input = spconv.SparseConvTensor(voxel_feats, voxel_coords.int(), spatial_shape, batch_size)
         self._mark('voxelize')
-        lvl_fusion = self._cfg(tc, 'lvl_fusion', False)
-        assert not lvl_fusion, 'lvl_fusion (SoftGroup++) is not built yet'
-        semantic_scores, pt_offsets, output_feats = self.forward_backbone(input, v2p_map, x4_split=x4_split)
+        # lvl_fusion (softgroup.py:309-312): the voxels themselves are level 1 of the pyramid -- heads, grouping and the
+        # instance branch run on voxel rows; results return to points through v2p_map
+        lvl_fusion = bool(self._cfg(tc, 'lvl_fusion', False))
+        semantic_scores, pt_offsets, output_feats = self.forward_backbone(input, v2p_map, x4_split=x4_split,
+                                                                          lvl_fusion=lvl_fusion)
         self._mark('backbone')
         inject = kwargs.get('inject_pointwise', None)
         if inject is not None:
@@ -185,6 +206,7 @@ class SoftGroup(nn.Module):
             # produce trained-quality point-wise predictions, so the heads' outputs -- already computed above at full
             # cost -- are overwritten by synthetic ones (one-hot*logit + N(0,1), centroid offsets + N(0,sigma)) to
             # give the grouping stage the load a trained checkpoint would. Never used by the drop-in forward.
+            assert not lvl_fusion, 'inject_pointwise carries point-level predictions'
             semantic_scores, pt_offsets = inject
         if x4_split:
             coords_float = self.merge_4_parts(coords_float)
@@ -207,12 +229,17 @@ class SoftGroup(nn.Module):
             if 'semantic' in eval_tasks:
                 fetch.add('coords_float', coords_float)
                 fetch.add('color_feats', color_feats)
-                fetch.add('semantic_preds', semantic_preds)
-                fetch.add('offset_preds', pt_offsets)
+                # get_point_wise_results (softgroup.py:524-536): voxel predictions go back to points under lvl_fusion
+                fetch.add('semantic_preds', semantic_preds[v2p_map.long()] if lvl_fusion else semantic_preds)
+                fetch.add('offset_preds', pt_offsets[v2p_map.long()] if lvl_fusion else pt_offsets)
                 fetch.add('offset_labels', pt_offset_labels)
         if not self.semantic_only and ('instance' in eval_tasks or 'panoptic' in eval_tasks):
+            if lvl_fusion:  # softgroup.py:332-334
+                batch_idxs = input.indices[:, 0].int().contiguous()
+                coords_float = voxelization(coords_float.contiguous(), p2v_map.contiguous())
             proposals_idx, proposals_offset = self.forward_grouping(semantic_scores, pt_offsets, batch_idxs,
-                                                                    coords_float, self.grouping_cfg)
+                                                                    coords_float, self.grouping_cfg,
+                                                                    lvl_fusion=lvl_fusion)
             self._mark('grouping')
             inst_feats, inst_map = self.clusters_voxelization(proposals_idx, proposals_offset, output_feats,
                                                               coords_float, **self._voxel_cfg())
@@ -220,7 +247,8 @@ class SoftGroup(nn.Module):
             _, cls_scores, iou_scores, mask_scores = self.forward_instance(inst_feats, inst_map)
             self._mark('instance_head')
             inst = self.get_instances(scan_ids[0] if scan_ids else None, proposals_idx, semantic_scores, cls_scores,
-                                      iou_scores, mask_scores, device_only=device_only)
+                                      iou_scores, mask_scores, v2p_map=v2p_map, lvl_fusion=lvl_fusion,
+                                      device_only=device_only)
             self._mark('get_instances')
             if device_only:
                 ret.update(device_instances=inst, proposals_idx=proposals_idx, proposals_offset=proposals_offset)
@@ -247,8 +275,12 @@ class SoftGroup(nn.Module):
     def forward_backbone(self, input, input_map, x4_split=False, lvl_fusion=False):
         """softgroup.py:363-378."""
         if x4_split:
+            assert not lvl_fusion, 'x4_split not support lvl_fusion'  # softgroup.py:365
             output_feats = self.forward_4_parts(input, input_map)
             output_feats = self.merge_4_parts(output_feats)
+        elif lvl_fusion:
+            output = self.output_layer(self.unet(self.input_conv(input)))
+            output_feats = output.features  # stays on voxel rows (softgroup.py:373-374)
         else:
             output = self.input_conv(input)
             output = self.unet(output)
@@ -311,7 +343,8 @@ class SoftGroup(nn.Module):
         npoint_thr = float(self._cfg(g, 'npoint_thr'))
         score_thr = float(self._cfg(g, 'score_thr'))
         if self._cfg(g, 'with_pyramid', False) or self._cfg(g, 'with_octree', False):
-            return self._forward_grouping_pp(scores, pt_offsets, batch_idxs, coords_float, batch_size)
+            return self._forward_grouping_pp(scores, pt_offsets, batch_idxs, coords_float, batch_size,
+                                             lvl_fusion=lvl_fusion)
         cnm = self._cfg(g, 'class_numpoint_mean')
         assert len(cnm) == self.semantic_classes
         ignore = set(self._cfg(g, 'ignore_classes', []))
@@ -352,7 +385,7 @@ class SoftGroup(nn.Module):
         return cidx, coff
 
     # ------------------------------------------------------------------------------------------------------
-    def _forward_grouping_pp(self, scores, pt_offsets, batch_idxs, coords_float, batch_size):
+    def _forward_grouping_pp(self, scores, pt_offsets, batch_idxs, coords_float, batch_size, lvl_fusion=False):
         """SoftGroup++ grouping (softgroup.py:427-463, 482-507): per class, optional pyramid re-voxelisation at
         base_size*level, octree ball query, clustering, inverse pyramid map -- every step on the GPU (the reference
         hashes on the CPU at :494 and builds a dense [nCluster, n] CPU matrix at :500-507). The radius and the level
@@ -385,8 +418,9 @@ class SoftGroup(nn.Module):
             if with_pyramid:
                 level = self.get_level(coords_.size(0))
                 radius = base_radius * level
-                coords_, pt_offsets_, batch_idxs_, l2p_map = self.pyramid_map(coords_, pt_offsets_, batch_idxs_, level,
-                                                                              base_size)
+                if level > 1 or not lvl_fusion:  # under lvl_fusion the rows already are level-1 voxels (:447)
+                    coords_, pt_offsets_, batch_idxs_, l2p_map = self.pyramid_map(coords_, pt_offsets_, batch_idxs_,
+                                                                                  level, base_size)
             batch_offsets_ = self.get_batch_offsets(batch_idxs_, batch_size)
             neighbor_inds, start_len = ball_query((coords_ + pt_offsets_).contiguous(), batch_idxs_.contiguous(),
                                                   batch_offsets_, radius, mean_active, with_octree=with_octree)
@@ -529,12 +563,19 @@ class SoftGroup(nn.Module):
         #{points of p with mask_score[:, i] > mask_score_thr} >= min_npoint."""
         if proposals_idx.size(0) == 0:
             return []
+        semantic_pred_rows = None
+        if lvl_fusion:
+            # the reference expands dense voxel masks with mask_pred[:, v2p_map.long()] (:560-561, :579-580) and counts
+            # POINTS for min_npoint; here the (proposal, voxel) entries themselves are expanded to (proposal, point)
+            proposals_idx, row_of = expand_voxel_entries(proposals_idx, v2p_map, semantic_scores.size(0))
+            mask_scores = mask_scores[row_of]
+            semantic_pred_rows = semantic_scores.max(1)[1][v2p_map.long()]
         tc = self.test_cfg
         mask_thr = float(self._cfg(tc, 'mask_score_thr'))
         cls_thr = float(self._cfg(tc, 'cls_score_thr'))
         min_npoint = int(self._cfg(tc, 'min_npoint'))
         num_instances = cls_scores.size(0)
-        num_points = semantic_scores.size(0)
+        num_points = v2p_map.numel() if lvl_fusion else semantic_scores.size(0)  # length of the output masks
         nI = self.instance_classes
         cls_sm = cls_scores.softmax(1)
         pid = proposals_idx[:, 0].long()
@@ -570,7 +611,7 @@ class SoftGroup(nn.Module):
         for i in range(nI):
             if i in self.sem2ins_classes:
                 if semantic_pred is None:
-                    semantic_pred = semantic_scores.max(1)[1]
+                    semantic_pred = semantic_pred_rows if lvl_fusion else semantic_scores.max(1)[1]
                 ids_i = (semantic_pred == i).nonzero().view(-1).cpu().numpy()
                 instances.append(dict(scan_id=scan_id, label_id=i + 1, conf=np.float32(1.),
                                       pred_mask=rle_encode_ids(ids_i, num_points)))
