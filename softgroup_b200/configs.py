@@ -53,9 +53,24 @@ _STPLS3D_PP = dict(  # configs/softgroup++/softgroup++_stpls3d.yaml:1-37 (lvl_fu
                   eval_tasks=['semantic', 'instance']),
     fixed_modules=[])
 
-CONFIGS = {'scannet': _SCANNET, 's3dis': _S3DIS, 'kitti': _KITTI, 'stpls3d++': _STPLS3D_PP}
+_SCANNET_PP = dict(  # configs/softgroup++/softgroup++_scannet.yaml:1-36 (the one config that tests with lvl_fusion)
+    channels=32, num_blocks=7, semantic_classes=20, instance_classes=18, sem2ins_classes=[], semantic_only=False,
+    ignore_label=-100,
+    grouping_cfg=dict(with_pyramid=True, pyramid_base_size=0.02, with_octree=True, score_thr=0.2, radius=0.04,
+                      mean_active=300,
+                      class_numpoint_mean=[-1., -1., 3917., 12056., 2303., 8331., 3948., 3166., 5629., 11719., 1003.,
+                                           3317., 4912., 10221., 3889., 4136., 2120., 945., 3967., 2589.],
+                      npoint_thr=0.05, ignore_classes=[0, 1]),
+    instance_voxel_cfg=dict(scale=50, spatial_shape=20),
+    train_cfg=dict(max_proposal_num=200, pos_iou_thr=0.5),
+    test_cfg=dict(lvl_fusion=True, x4_split=False, cls_score_thr=0.001, mask_score_thr=-0.5, min_npoint=100,
+                  eval_tasks=['semantic', 'instance']),
+    fixed_modules=[])
+
+CONFIGS = {'scannet': _SCANNET, 's3dis': _S3DIS, 'kitti': _KITTI, 'stpls3d++': _STPLS3D_PP, 'scannet++': _SCANNET_PP}
 # which synthetic shape (softgroup_b200.synth.SHAPES) goes with which config
-SHAPE_OF = {'scannet': 'c2_scannet', 's3dis': 'c3_s3dis', 'kitti': 'c4_kitti', 'stpls3d++': 'c5_stpls3d'}
+SHAPE_OF = {'scannet': 'c2_scannet', 's3dis': 'c3_s3dis', 'kitti': 'c4_kitti', 'stpls3d++': 'c5_stpls3d',
+            'scannet++': 'c2_scannet'}
 
 
 def model_cfg(name='scannet', **overrides):

@@ -82,7 +82,8 @@ def test_rle_encode_many_empty():
 @pytest.mark.parametrize('name,path', [('scannet', 'configs/softgroup/softgroup_scannet.yaml'),
                                        ('s3dis', 'configs/softgroup/softgroup_s3dis_fold5.yaml'),
                                        ('kitti', 'configs/softgroup/softgroup_kitti.yaml'),
-                                       ('stpls3d++', 'configs/softgroup++/softgroup++_stpls3d.yaml')])
+                                       ('stpls3d++', 'configs/softgroup++/softgroup++_stpls3d.yaml'),
+                                       ('scannet++', 'configs/softgroup++/softgroup++_scannet.yaml')])
 def test_configs_match_reference_yaml(name, path):
     import yaml
     ref = yaml.safe_load(open(os.path.join(REF, path)))['model']
