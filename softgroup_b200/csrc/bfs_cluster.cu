@@ -89,6 +89,40 @@ __global__ void bfs_propagate_kernel(const int32_t *__restrict__ idxs, const int
   if (__any_sync(0xffffffffu, changed) && lane == 0) w.scalars[0] = 1;
 }
 
+// Round-2 candidate (off by default, sgb_test_set_bfs_mode(1)): same least fixed point, but a node re-reads its list
+// only when its (chased) label is lower than the one it pushed last time. `w.wins` (idle until the emit phase) keeps
+// the last pushed label. Every pass still chases every node's label (2-3 words per node); the 4 bytes per edge are
+// read once per CHANGE of the source label instead of once per pass. The pass in which nobody pushes ends the loop:
+// then label[v] <= pushed[u] <= label[u] for every edge u->v, which is the fixed point of the full iteration.
+__global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len,
+                                              int N, BfsWs w, int first_pass) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  volatile int32_t *label = w.label;
+  bool pushed_any = false;
+  for (int u = warp; u < N; u += nwarps) {
+    int lu = label[u];
+    while (true) {
+      int l2 = label[lu];
+      if (l2 >= lu) break;
+      lu = l2;
+    }
+    if (lane == 0 && lu < label[u]) atomicMin(&w.label[u], lu);
+    const int prev = first_pass ? 0x7fffffff : *(volatile int32_t *)&w.wins[u];
+    if (lu >= prev) continue;  // warp-uniform: nothing new to tell the out-neighbours
+    pushed_any = true;
+    int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+    for (int j = lane; j < l; j += 32) {
+      int v = __ldg(&idxs[(size_t)s + j]);
+      if (label[v] > lu) atomicMin(&w.label[v], lu);
+    }
+    __syncwarp();
+    if (lane == 0) w.wins[u] = lu;
+  }
+  if (pushed_any && lane == 0) w.scalars[0] = 1;
+}
+
 __global__ void bfs_size_kernel(int N, const int32_t *__restrict__ start_len, BfsWs w) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = v < N;
@@ -406,7 +440,11 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
 
 using namespace sgb;
 
+static int g_bfs_mode = 0;  // 0: full propagation passes (validated), 1: frontier passes (round-2 candidate)
+
 extern "C" {
+
+void sgb_test_set_bfs_mode(int mode) { g_bfs_mode = mode; }
 
 size_t sgb_bfs_cluster_workspace_bytes(int N) {
   if (N < 0) N = 0;
@@ -435,7 +473,10 @@ int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_sta
   int grid = std::min(div_up((long long)N * 32, 256), kNumSMs * 16);
   for (int it = 0; it < 100000; it++) {
     SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 4, st));
-    bfs_propagate_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w);
+    if (g_bfs_mode == 1)
+      bfs_propagate_frontier_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w, it == 0);
+    else
+      bfs_propagate_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w);
     SGB_LAUNCH_CHECK();
     int changed = 0;
     SGB_CUDA_CHECK(cudaMemcpyAsync(&changed, w.scalars, 4, cudaMemcpyDeviceToHost, st));

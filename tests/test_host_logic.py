@@ -146,3 +146,53 @@ def test_synth_scan_layout(shape):
     x4 = synth.to_x4_split(a)
     assert x4['batch_size'] == 4 and np.array_equal(np.sort(x4['x4_order']), np.arange(n))
     assert set(np.unique(x4['coords'][:, 0])) == {0, 1, 2, 3}
+
+
+# ---- bfs_cluster labelling: sequential emulation of the frontier iteration (bfs_cluster.cu) ---------------------
+def _reference_seed_labels(lists):
+    """bfs_cluster.cpp:33-126 semantics: seeds in index order, BFS over the DIRECTED out-lists, first claim wins."""
+    n = len(lists)
+    label = [-1] * n
+    for i in range(n):
+        if label[i] >= 0:
+            continue
+        label[i] = i
+        queue = [i]
+        while queue:
+            u = queue.pop(0)
+            for v in lists[u]:
+                if label[v] < 0:
+                    label[v] = i
+                    queue.append(v)
+    return label
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_frontier_label_iteration_reaches_reference_labels(seed):
+    """label[v] = smallest index that can reach v; a node re-pushes only when its chased label dropped below the one
+    it pushed last (`pushed`), and the pass without a push ends the loop -- in any processing order."""
+    rng = np.random.RandomState(seed)
+    n = 300
+    pts = rng.rand(n, 2) * (1.0 if seed % 2 else 3.0)
+    d = ((pts[:, None] - pts[None]) ** 2).sum(-1)
+    cap = 6  # truncation to the first `cap` neighbours by index makes the graph asymmetric, like the 1000 cap
+    lists = [list(np.nonzero(d[u] < 0.02)[0][:cap]) for u in range(n)]
+    want = _reference_seed_labels(lists)
+    label = list(range(n))
+    pushed = [2**31 - 1] * n
+    for _ in range(10 * n):
+        any_push = False
+        for u in rng.permutation(n):  # arbitrary order stands in for the GPU's scheduling
+            lu = label[u]
+            while label[lu] < lu:
+                lu = label[lu]
+            label[u] = min(label[u], lu)
+            if lu >= pushed[u]:
+                continue
+            any_push = True
+            for v in lists[u]:
+                label[v] = min(label[v], lu)
+            pushed[u] = lu
+        if not any_push:
+            break
+    assert label == want
