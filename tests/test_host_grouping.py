@@ -1,0 +1,189 @@
+"""forward_grouping host logic on CPU: the one-launch segmented restructure (softgroup_b200/model/softgroup.py) against
+the reference's per-class loop (softgroup/model/softgroup.py:411-480). The two device ops it calls are replaced by
+stand-ins built on the oracle (the CPU checker), so only the Python restructuring is under test here -- class-major
+entry order, segment ids, per-segment thresholds in float32, index mapping back to points, proposal concatenation."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from softgroup_b200 import synth
+from softgroup_b200.configs import model_cfg
+from softgroup_b200.model import SoftGroup
+from softgroup_b200.model import softgroup as sg_module
+
+
+def _fake_ballquery_nosync(coords, batch_idxs, batch_offsets, radius):
+    idx, sl = oracle.ballquery_batch_p(coords.numpy(), batch_idxs.numpy(), batch_offsets.numpy(), radius)
+    return (torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(sl.astype(np.int32)),
+            torch.tensor([idx.size], dtype=torch.int32))
+
+
+def _fake_bfs_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, symmetric=False, nactive=None):
+    """bfs_cluster.cpp:33-126 over the whole node set with a per-seed-segment threshold (what the library computes)."""
+    idxs, sl = ball_query_idxs.numpy(), start_len.numpy()
+    n = sl.shape[0]
+    seen = np.zeros(n, bool)
+    cl, offs = [], [0]
+    for i in range(n):
+        if seen[i]:
+            continue
+        seen[i] = True
+        queue, comp = [i], []
+        while queue:
+            u = queue.pop(0)
+            comp.append(u)
+            for v in idxs[sl[u, 0]:sl[u, 0] + sl[u, 1]]:
+                if not seen[v]:
+                    seen[v] = True
+                    queue.append(int(v))
+        t = np.float32(thr) if node_seg is None else np.float32(seg_thr[node_seg[i]])
+        if np.float32(len(comp)) >= t:
+            cid = len(offs) - 1
+            cl += [(cid, u) for u in comp]
+            offs.append(offs[-1] + len(comp))
+    return (torch.tensor(cl, dtype=torch.int32).reshape(-1, 2), torch.tensor(offs, dtype=torch.int32))
+
+
+def reference_forward_grouping(model, semantic_scores, pt_offsets, batch_idxs, coords_float):
+    """The reference's loop, ops taken from the oracle (ballquery_batch_p: bfs_cluster.cu:15-101 restatement,
+    bfs_cluster: the compiled reference's algorithm)."""
+    g = model.grouping_cfg
+    get = model._cfg
+    bs = int(batch_idxs.max()) + 1
+    scores = torch.from_numpy(semantic_scores).softmax(-1).numpy()
+    mean = np.asarray(get(g, 'class_numpoint_mean'), np.float32)
+    idx_list, off_list = [], []
+    for class_id in range(model.semantic_classes):
+        if class_id in get(g, 'ignore_classes'):
+            continue
+        obj = np.nonzero(scores[:, class_id] > get(g, 'score_thr'))[0]
+        if obj.size < get(model.test_cfg, 'min_npoint'):
+            continue
+        b = batch_idxs[obj].astype(np.int32)
+        boff = np.zeros(bs + 1, np.int32)
+        boff[1:] = np.cumsum(np.bincount(b, minlength=bs))
+        xyz = (coords_float[obj] + pt_offsets[obj]).astype(np.float32)
+        nb, sl = oracle.ballquery_batch_p(xyz, b, boff, get(g, 'radius'))
+        pidx, poff = oracle.bfs_cluster(mean, nb, sl, get(g, 'npoint_thr'), class_id)
+        pidx = pidx.copy()
+        pidx[:, 1] = obj[pidx[:, 1]]
+        if off_list:
+            pidx[:, 0] += sum(len(x) for x in off_list) - 1
+            poff = (poff + off_list[-1][-1])[1:]
+        if pidx.shape[0] > 0:
+            idx_list.append(pidx)
+            off_list.append(poff)
+    if not idx_list:
+        return np.zeros((0, 2), np.int32), np.zeros((0, ), np.int32)
+    return np.concatenate(idx_list), np.concatenate(off_list)
+
+
+@pytest.mark.parametrize('seed,batch', [(0, 1), (1, 1), (2, 2)])
+def test_forward_grouping_equals_reference_loop(monkeypatch, seed, batch):
+    monkeypatch.setattr(sg_module, 'ballquery_batch_p_nosync', _fake_ballquery_nosync)
+    monkeypatch.setattr(sg_module, 'bfs_cluster_segments', _fake_bfs_segments)
+    model = SoftGroup(**model_cfg('scannet', channels=16, num_blocks=2, test_cfg=dict(min_npoint=30))).eval()
+    parts = [synth.make_scan('c1_plumbing', seed=seed * 10 + b, n_points=1500) for b in range(batch)]
+    scores, offs, coords, bidx = [], [], [], []
+    for b, sc in enumerate(parts):
+        s, o = synth.grouping_inputs(sc, sigma=0.03, seed=seed)
+        # a few confused points so that some classes fall under min_npoint and some points pass two classes
+        rng = np.random.RandomState(seed)
+        flip = rng.choice(s.shape[0], 60, replace=False)
+        s[flip, rng.randint(2, 20, 60)] += 9.0
+        scores.append(s)
+        offs.append(o)
+        coords.append(sc['coords_float'])
+        bidx.append(np.full(s.shape[0], b, np.int32))
+    scores, offs, coords, bidx = map(np.concatenate, (scores, offs, coords, bidx))
+    got_idx, got_off = model.forward_grouping(torch.from_numpy(scores), torch.from_numpy(offs), torch.from_numpy(bidx),
+                                              torch.from_numpy(coords))
+    want_idx, want_off = reference_forward_grouping(model, scores, offs, bidx, coords)
+    assert want_off.size > 2, 'the case must produce several proposals'
+    assert np.array_equal(got_idx.numpy(), want_idx)
+    assert np.array_equal(got_off.numpy(), want_off)
+
+
+# ---- SoftGroup++ grouping (pyramid re-voxelisation + octree ball query), with and without lvl_fusion ------------
+def _fake_ball_query(coords, batch_idxs, batch_offsets, radius, mean_active, with_octree=False):
+    if with_octree:
+        idx, sl = oracle.octree_ball_query(coords.numpy(), mean_active, radius)
+    else:
+        idx, sl = oracle.ballquery_batch_p(coords.numpy(), batch_idxs.numpy(), batch_offsets.numpy(), radius)
+    return torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(sl.astype(np.int32))
+
+
+def _fake_voxelization(feats, map_rule, mode=4):
+    return torch.from_numpy(oracle.voxelization(feats.numpy(), map_rule.numpy(), mode))
+
+
+def reference_forward_grouping_pp(model, semantic_scores, pt_offsets, batch_idxs, coords_float, lvl_fusion):
+    """softgroup.py:411-507 with the dense [nCluster, n] inverse map of :500-507."""
+    g = model.grouping_cfg
+    get = model._cfg
+    bs = int(batch_idxs.max()) + 1
+    scores = torch.from_numpy(semantic_scores).softmax(-1).numpy()
+    mean = np.asarray(get(g, 'class_numpoint_mean'), np.float32)
+    base = get(g, 'pyramid_base_size')
+    idx_list, off_list = [], []
+    for class_id in range(model.semantic_classes):
+        if class_id in get(g, 'ignore_classes'):
+            continue
+        obj = np.nonzero(scores[:, class_id] > get(g, 'score_thr'))[0]
+        if obj.size < get(model.test_cfg, 'min_npoint'):
+            continue
+        b = batch_idxs[obj].astype(np.int32)
+        xyz, off = coords_float[obj], pt_offsets[obj]
+        level = model.get_level(obj.size)
+        radius = get(g, 'radius') * level
+        l2p = None
+        if level > 1 or not lvl_fusion:
+            vc = np.concatenate([b[:, None].astype(np.int64), (torch.from_numpy(xyz) / (base * level)).long().numpy()], 1)
+            vcoords, l2p, p2l = oracle.voxelization_idx(vc, int(b[-1]) + 1, 4)
+            n_before = obj.size
+            xyz = oracle.voxelization(xyz, p2l, 4)
+            off = oracle.voxelization(off, p2l, 4)
+            b = vcoords[:, 0].astype(np.int32)
+        boff = np.zeros(bs + 1, np.int32)
+        boff[1:] = np.cumsum(np.bincount(b, minlength=bs))
+        nb, sl = oracle.octree_ball_query((xyz + off).astype(np.float32), get(g, 'mean_active'), radius)
+        pidx, poff = oracle.bfs_cluster(mean, nb, sl, get(g, 'npoint_thr'), class_id)
+        if l2p is not None:
+            dense = np.zeros((poff.size - 1, xyz.shape[0]), np.int32)
+            dense[pidx[:, 0], pidx[:, 1]] = 1
+            dense = dense[:, l2p.astype(np.int64)]
+            assert dense.shape[1] == n_before
+            pidx = np.stack(np.nonzero(dense), 1).astype(np.int32)
+            poff = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.int32)
+        pidx = pidx.copy()
+        pidx[:, 1] = obj[pidx[:, 1]]
+        if off_list:
+            pidx[:, 0] += sum(len(x) for x in off_list) - 1
+            poff = (poff + off_list[-1][-1])[1:]
+        if pidx.shape[0] > 0:
+            idx_list.append(pidx)
+            off_list.append(poff)
+    if not idx_list:
+        return np.zeros((0, 2), np.int32), np.zeros((0, ), np.int32)
+    return np.concatenate(idx_list), np.concatenate(off_list)
+
+
+@pytest.mark.parametrize('lvl_fusion', [False, True])
+def test_forward_grouping_pp_equals_reference_loop(monkeypatch, lvl_fusion):
+    monkeypatch.setattr(sg_module, 'ball_query', _fake_ball_query)
+    monkeypatch.setattr(sg_module, 'bfs_cluster_segments', _fake_bfs_segments)
+    monkeypatch.setattr(sg_module, 'voxelization', _fake_voxelization)
+    cfg = model_cfg('scannet++', channels=16, num_blocks=2, test_cfg=dict(min_npoint=30))
+    cfg['grouping_cfg'].update(pyramid_base_size=0.02, radius=0.04)
+    model = SoftGroup(**cfg).eval()
+    model.get_level = lambda n: 2 if n > 250 else 1  # both levels at a size the CPU oracle handles
+    sc = synth.make_scan('c1_plumbing', seed=5, n_points=2500)
+    scores, offs = synth.grouping_inputs(sc, sigma=0.03, seed=5)
+    coords, bidx = sc['coords_float'], np.zeros(scores.shape[0], np.int32)
+    got_idx, got_off = model.forward_grouping(torch.from_numpy(scores), torch.from_numpy(offs), torch.from_numpy(bidx),
+                                              torch.from_numpy(coords), lvl_fusion=lvl_fusion)
+    want_idx, want_off = reference_forward_grouping_pp(model, scores, offs, bidx, coords, lvl_fusion)
+    assert want_off.size > 2
+    assert np.array_equal(got_idx.numpy(), want_idx)
+    assert np.array_equal(got_off.numpy(), want_off)
