@@ -187,3 +187,48 @@ def test_forward_grouping_pp_equals_reference_loop(monkeypatch, lvl_fusion):
     assert want_off.size > 2
     assert np.array_equal(got_idx.numpy(), want_idx)
     assert np.array_equal(got_off.numpy(), want_off)
+
+
+# ---- clusters_voxelization (softgroup.py:655-709): per-cluster rescaling to the 20^3 grid + hashing -------------
+def _fake_sec(fn):
+    return lambda inp, offsets: torch.from_numpy(fn(inp.numpy(), offsets.numpy()))
+
+
+def test_clusters_voxelization_equals_reference_steps(monkeypatch):
+    monkeypatch.setattr(sg_module, 'sec_min', _fake_sec(oracle.sec_min))
+    monkeypatch.setattr(sg_module, 'sec_max', _fake_sec(oracle.sec_max))
+    monkeypatch.setattr(sg_module, 'voxelization', _fake_voxelization)
+    model = SoftGroup(**model_cfg('scannet', channels=16, num_blocks=2)).eval()
+    rng = np.random.RandomState(0)
+    n, nprop, C = 2000, 9, 16
+    coords = (rng.rand(n, 3) * np.array([4.0, 3.0, 2.0])).astype(np.float32)
+    feats = rng.randn(n, C).astype(np.float32)
+    lens = rng.randint(20, 300, nprop)
+    lens[3] = 1  # a single-point cluster: zero extent -> scale clamps to the cap
+    members = [rng.choice(n, ln, replace=False) for ln in lens]
+    pidx = np.concatenate([np.stack([np.full(len(m), p), m], 1) for p, m in enumerate(members)]).astype(np.int32)
+    poff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    scale, S = 50, 20
+    x, inp_map = model.clusters_voxelization(torch.from_numpy(pidx), torch.from_numpy(poff), torch.from_numpy(feats),
+                                             torch.from_numpy(coords), scale=scale, spatial_shape=S)
+    # the reference's steps, line by line, on torch CPU + oracle ops
+    bi = torch.from_numpy(pidx[:, 0]).long()
+    ci = torch.from_numpy(pidx[:, 1]).long()
+    f = torch.from_numpy(feats)[ci]
+    c = torch.from_numpy(coords)[ci]
+    cmin = torch.from_numpy(oracle.sec_min(c.numpy(), poff))
+    cmax = torch.from_numpy(oracle.sec_max(c.numpy(), poff))
+    cs = 1 / ((cmax - cmin) / S).max(1)[0] - 0.01
+    cs = torch.clamp(cs, min=None, max=scale)
+    cmin = cmin * cs[:, None]
+    cs = cs[bi]
+    c = c * cs[:, None]
+    c -= cmin[bi]
+    assert c.shape.numel() == ((c >= 0) * (c < S)).sum()
+    c = torch.cat([bi.view(-1, 1), c.long()], 1)
+    oc, imap, omap = oracle.voxelization_idx(c.numpy(), nprop, 4)
+    of = oracle.voxelization(f.numpy(), omap, 4)
+    assert np.array_equal(x.indices.numpy(), oc.astype(np.int32)) and x.batch_size == nprop
+    assert list(x.spatial_shape) == [S] * 3
+    assert np.array_equal(inp_map.numpy(), imap)
+    assert np.array_equal(x.features.numpy(), of)
