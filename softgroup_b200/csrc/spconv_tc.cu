@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace sgb {
 
@@ -51,76 +52,6 @@ struct TcArgs {
   long long *dbg;  // optional timeline buffer (test hook)
   int skip;        // test hook (timing decomposition only, results are garbage): 1 no tcgen05.st, 2 no MMA, 4 no gather, 8 no weight copy
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
-      "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
-      "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor: core matrix = 8 rows x 16 B (128 contiguous bytes);
-// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // upper half <- first source
-  return *reinterpret_cast<__half2 *>(&r);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
 
 // Warp roles: warps 0-3 = producer group 0, warps 4-7 = producer group 1 (one output row per thread; group g fills slot g
 // of every iteration pair), warp 8 = MMA issuer (warp-uniform, one elected lane), warp 9 = weight loader (TMA bulk copies).
@@ -788,76 +719,4 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
-}
-
-// ---- micro-benchmark hook: cost of back-to-back tcgen05.mma kind::tf32 (M=128, N, K=8) into one accumulator ----
-namespace sgb {
-__global__ void umma_rate_kernel(int N, int reps, int per_commit, long long *out, int a_in_tmem) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ uint32_t s_tmem;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (16384 + 256 * 32 * 4) / 4; i += blockDim.x) reinterpret_cast<float *>(smem)[i] = 0.f;
-  if (tid == 0) {
-    mbar_init(smem_u32(&bar), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = s_tmem;
-  if (tid == 0) {
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
-    uint64_t da = umma_desc(smem_u32(smem), 2048, 128);
-    uint64_t db = umma_desc(smem_u32(smem + 16384), (uint32_t)N * 16, 128);
-    long long t0 = clock64();
-    uint32_t phase = 0;
-    for (int r = 0; r < reps; r += per_commit) {
-      if (a_in_tmem >= 100) {
-        // kind::f16 issue patterns of the conv kernel, nt = N: 100 = [N=2nt at D | N=nt at D+nt] (overlapping accumulators),
-        // 101 = three N=nt products into ONE accumulator, 102 = [N=2nt at D | N=nt at a disjoint accumulator]
-        const uint32_t i1 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
-        const uint32_t i2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | (8u << 24);
-        for (int k = 0; k < per_commit; k++) {
-          const uint32_t ta = tmem + 384 + 8 * (k & 7);
-          if (a_in_tmem == 100) {
-            umma_f16_ts(tmem, ta, db, i2, 1u);
-            umma_f16_ts(tmem + N, ta + 16, db, i1, 1u);
-          } else if (a_in_tmem == 101) {
-            umma_f16_ts(tmem, ta, db, i1, 1u);
-            umma_f16_ts(tmem, ta + 16, db, i1, 1u);
-            umma_f16_ts(tmem, ta, db, i1, 1u);
-          } else {
-            umma_f16_ts(tmem, ta, db, i2, 1u);
-            umma_f16_ts(tmem + 256, ta + 16, db, i1, 1u);
-          }
-        }
-      } else if (a_in_tmem > 0) {
-        for (int k = 0; k < per_commit; k++) umma_f16_ts(tmem + 64 * (k % a_in_tmem), tmem + 256 + 8 * (k & 7), db, idesc, 1u);
-      } else {
-        for (int k = 0; k < per_commit; k++) umma_tf32(tmem + 64 * (k % (-a_in_tmem + 1)), da, db, idesc, 1u);
-      }
-      umma_commit(smem_u32(&bar));
-      mbar_wait(smem_u32(&bar), phase);
-      phase ^= 1;
-    }
-    long long t1 = clock64();
-    out[0] = t1 - t0;
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-}
-}  // namespace sgb
-
-extern "C" int sgb_test_umma_rate(int N, int reps, int per_commit, long long *d_out, void *stream, int a_in_tmem) {
-  SGB_CUDA_CHECK(cudaFuncSetAttribute(sgb::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  sgb::umma_rate_kernel<<<1, 128, 16384 + 256 * 32 * 4, (cudaStream_t)stream>>>(N, reps, per_commit, d_out, a_in_tmem);
-  SGB_LAUNCH_CHECK();
-  return SGB_OK;
 }
