@@ -5,6 +5,10 @@ import this package. The product (softgroup_b200) never does; it fails loudly wh
 library is missing instead of falling back to anything in here.
 
 numpy in / numpy out, function names follow softgroup/ops/functions.py of the reference.
+
+Files: sg_oracle.c (the ops, plain C), spconv_oracle.py (sparse convolution restatement, numpy), build_ref.py (compiles
+the unmodified reference ops into oracle/_ref), spconv_cpu.py + ops_cpu.py (module / function plumbing that lets the
+unmodified reference MODEL code run on the CPU to generate whole-model golden vectors, tests/golden/).
 """
 import ctypes
 import os
