@@ -86,3 +86,42 @@ def test_vs_reference_fresh(ref_ops):
         ref_ops.bfs_cluster(torch.from_numpy(mean), torch.from_numpy(idx), torch.from_numpy(sl), ci, co, n, 2.0, 0)
         oi, oo = oracle.bfs_cluster(mean, idx, sl, 2.0, 0)
         assert np.array_equal(oi, ci.numpy().reshape(-1, 2)) and np.array_equal(oo, co.numpy())
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_vs_reference_fresh_more(ref_ops, seed):
+    """More fresh-input comparisons with the compiled reference: batched hashing with duplicates and empty batches,
+    class-mean (relative) BFS thresholds, octree build on clustered points."""
+    if ref_ops is None:
+        pytest.skip('oracle/_ref not built')
+    rng = np.random.RandomState(100 + seed)
+    # voxelize_idx: 3 batch items (one empty), heavy duplication, every mode
+    n = 4000
+    b = rng.choice([0, 2], n)  # batch item 1 stays empty
+    xyz = rng.randint(0, 12, (n, 3))
+    coords = np.concatenate([b[:, None], xyz], 1).astype(np.int64)
+    coords = coords[np.argsort(b, kind='stable')]
+    for mode in (1, 2, 3, 4):
+        c = torch.from_numpy(coords)
+        oc, im, om = c.new(), torch.IntTensor(c.size(0)).zero_(), torch.IntTensor()
+        ref_ops.voxelize_idx(c, oc, im, om, 3, mode)
+        a, bb, d = oracle.voxelization_idx(coords, 3, mode)
+        assert np.array_equal(a, oc.numpy()) and np.array_equal(bb, im.numpy()) and np.array_equal(d, om.numpy()), mode
+    # bfs_cluster with relative thresholds (threshold * class mean, bfs_cluster.cpp:70-77) on ball-query graphs
+    pts = (rng.rand(700, 3) * np.array([1.0, 1.0, 0.3])).astype(np.float32)
+    idx, sl = oracle.ballquery_batch_p(pts, np.zeros(700, np.int32), np.array([0, 700], np.int32), 0.09)
+    mean = np.full(20, -1, np.float32)
+    mean[5] = 40.0
+    for thr, cls in [(0.5, 5), (2.0, 5), (3.0, 0)]:
+        ci, co = torch.IntTensor(), torch.IntTensor()
+        ref_ops.bfs_cluster(torch.from_numpy(mean), torch.from_numpy(idx), torch.from_numpy(sl), ci, co, 700, thr, cls)
+        oi, oo = oracle.bfs_cluster(mean, idx, sl, thr, cls)
+        assert np.array_equal(oi, ci.numpy().reshape(-1, 2)) and np.array_equal(oo, co.numpy()), (thr, cls)
+    # octree build (octree_ball_query.cpp:19-165)
+    cl = (rng.randn(3000, 3) * 0.2 + rng.randint(0, 4, (3000, 1))).astype(np.float32)
+    boxes, pt_inds, psl = oracle.build_octree(cl)
+    rb, rp, rs = torch.zeros(585, 6), torch.zeros(3000, dtype=torch.int32), torch.zeros(512, 2, dtype=torch.int32)
+    mx, mn = cl.max(0), cl.min(0)  # the Python wrapper passes (centre, extent) of the cloud (functions.py:19-24)
+    xyzwhl = torch.from_numpy(np.concatenate([(mx + mn) / np.float32(2), mx - mn]).astype(np.float32))
+    ref_ops.build_and_export_octree(torch.from_numpy(cl), xyzwhl, rb, rp, rs, 3)
+    assert np.array_equal(boxes, rb.numpy()) and np.array_equal(pt_inds, rp.numpy()) and np.array_equal(psl, rs.numpy())
