@@ -209,6 +209,9 @@ int sgb_spconv_forward(const float *d_in, int in_stride, int in_off, const int32
  * in_packed != 0: d_in holds rows already activated and split by sgb_act_split (d_in_scale/d_in_shift must be NULL,
  * in_stride and in_off multiples of 32 words). */
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout);
+/* log2 of the factor the fp16 remainders are carried with: lo = fp16((x - hi) * 2^shift) for weights (host packer) and
+ * activations (sgb_act_split / in-kernel split); the kernel scales the correction products back. 0 in this build. */
+int sgb_spconv_tc_lo_shift(void);
 int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
                           const float *d_Wp, int Cin, int Cout, const float *d_in_scale, const float *d_in_shift,
                           const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,

@@ -33,6 +33,12 @@ namespace sgb {
 constexpr int TC_ROWS = 128;
 constexpr int TC_KC = 32;  // channels per stage
 constexpr int TC_THREADS = 320;  // 8 producer warps + 1 MMA warp + 1 weight-loader warp
+// The remainder lo = x - fp16(x) is carried as fp16(lo * 2^kLoShift); the correction columns are scaled back by
+// 2^-kLoShift when they are added to the main product. 0 = validated behaviour (lo is a subnormal fp16 for |x| < ~0.1:
+// 2^-25 absolute error); 11 removes the subnormal range and is the round-2 candidate (sgb_spconv_tc_lo_shift() tells
+// the host packer which one the library was built with).
+constexpr int kLoShift = 0;
+constexpr float kLoScale = (float)(1 << kLoShift), kLoInv = 1.0f / kLoScale;
 constexpr int BAR_FULL = 0, BAR_FREE = 3, BAR_BFULL = 9;  // per pair stage (<= 3); bars[8] = accumulator done
 
 struct TcArgs {
@@ -296,7 +302,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
           }
           const __half2 h01 = f2h2_sat(x.x, x.y), h23 = f2h2_sat(x.z, x.w);
           const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const __half2 l01 = f2h2_sat(x.x - f01.x, x.y - f01.y), l23 = f2h2_sat(x.z - f23.x, x.w - f23.y);
+          const __half2 l01 = f2h2_sat((x.x - f01.x) * kLoScale, (x.y - f01.y) * kLoScale),
+                        l23 = f2h2_sat((x.z - f23.x) * kLoScale, (x.w - f23.y) * kLoScale);
           hv[2 * q] = *reinterpret_cast<const uint32_t *>(&h01);
           hv[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&h23);
           lv[2 * q] = *reinterpret_cast<const uint32_t *>(&l01);
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-          const float x = __uint_as_float(v[e]) + __uint_as_float(c[e]);
+          const float x = fmaf(__uint_as_float(c[e]), kLoInv, __uint_as_float(v[e]));
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(pbuf + (uint32_t)(((cb + e) * TC_ROWS + lane_grp * 32 + lane) * 4)), "f"(x) : "memory");
         }
       }
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
                      : "r"(taddr + (uint32_t)nt));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(c[e]));
+        for (int e = 0; e < 8; e++) v[e] = __float_as_uint(fmaf(__uint_as_float(c[e]), kLoInv, __uint_as_float(v[e])));
       } else {
 #pragma unroll
         for (int e = 0; e < 8; e++) v[e] = 0u;
@@ -588,7 +595,7 @@ __global__ void act_split_kernel(const float *__restrict__ x, int x_stride, int 
   }
   const __half2 h = f2h2_sat(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = f2h2_sat(a - hf.x, b - hf.y);
+  const __half2 l = f2h2_sat((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
   const int chunk = c >> 5, w = (c & 31) >> 1;  // word index inside the chunk's hi block
   uint32_t *yr = y + (size_t)row * Cpad + chunk * 32;
   yr[w] = *reinterpret_cast<const uint32_t *>(&h);
@@ -621,6 +628,9 @@ int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scal
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
+
+// log2 of the factor the fp16 remainders (weights AND activations) are scaled by; the host packer must use the same.
+int sgb_spconv_tc_lo_shift(void) { return sgb::kLoShift; }
 
 // Packed weight size in floats for sgb_spconv_forward_tc: K * ceil(Cin/32) * 8 * N * 4 with N = Cout rounded to 16.
 long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout) {

@@ -54,6 +54,7 @@ SIGNATURES = {
     'sgb_spconv_tc_packed_floats': (c_longlong, [c_int, c_int, c_int]),
     'sgb_spconv_forward_tc': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, c_int, _P,
                                       _P, c_int, c_int, c_int, _P]),
+    'sgb_spconv_tc_lo_shift': (c_int, []),
     'sgb_act_split': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),

@@ -148,7 +148,8 @@ CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores
 
 def pack_weight_tc(W):
     """[K, Cin, Cout] f32 -> packed fp16 split for sgb_spconv_forward_tc (layout in sgb200.h):
-    [K, nkc, 4 chunks, 2 (hi, lo), N, 8 halves], hi = fp16(W), lo = fp16(W - hi); returned as a float32-typed buffer."""
+    [K, nkc, 4 chunks, 2 (hi, lo), N, 8 halves], hi = fp16(W), lo = fp16((W - hi) * 2^sgb_spconv_tc_lo_shift());
+    returned as a float32-typed buffer."""
     K, Cin, Cout = W.shape
     N = (Cout + 15) // 16 * 16
     nkc = (Cin + 31) // 32
@@ -156,7 +157,7 @@ def pack_weight_tc(W):
     Wp[:, :Cin, :Cout] = W
     Wp = Wp.view(K, nkc, 4, 8, N).permute(0, 1, 2, 4, 3).contiguous()  # [K, nkc, 4, N, 8]
     hi = Wp.half()
-    lo = (Wp - hi.float()).half()
+    lo = ((Wp - hi.float()) * float(2 ** _lib.lib().sgb_spconv_tc_lo_shift())).half()  # same scaling as the kernels
     packed = torch.stack([hi, lo], dim=3).contiguous()  # [K, nkc, 4, 2, N, 8] fp16
     return packed.view(torch.float32)
 
