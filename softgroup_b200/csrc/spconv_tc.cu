@@ -604,12 +604,13 @@ __global__ void act_split_kernel(const float *__restrict__ x, int x_stride, int 
 }  // namespace sgb
 
 static long long *g_tc_dbg = nullptr;
-static int g_tc_prefetch = 0, g_tc_maxb = 3, g_tc_maxsplit = 8, g_tc_skip = 0;
+static int g_tc_prefetch = 0, g_tc_maxb = 3, g_tc_maxsplit = 8, g_tc_skip = 0, g_tc_split_policy = 0;
 
 extern "C" {
 
 void sgb_test_set_tc_debug(long long *d_buf) { g_tc_dbg = d_buf; }
 void sgb_test_set_tc_skip(int mask) { g_tc_skip = mask; }
+void sgb_test_set_tc_split_policy(int policy) { g_tc_split_policy = policy; }  // 0: validated heuristic, 1: wave-aware
 // test/bench hook: weight prefetch on/off, most pair stages in the ring (1..3), largest split-K cluster (1 = off)
 void sgb_test_set_tc_tuning(int prefetch, int max_pairs, int max_ksplit) {
   g_tc_prefetch = prefetch;
@@ -699,6 +700,19 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   if (ctas * 2 <= kNumSMs && p.tmem_cols == 256 && (size_t)p.nbstages * bstage >= (size_t)NT * TC_ROWS * 4) {
     S = std::min({g_tc_maxsplit, 2 * kNumSMs / ctas, std::max(1, K * nkc / 4)});
     S = std::max(S, 1);
+  } else if (g_tc_split_policy == 1 && p.tmem_cols == 256 && (size_t)p.nbstages * bstage >= (size_t)NT * TC_ROWS * 4) {
+    // round-2 candidate (off by default): wave quantisation. With 2 CTAs per SM there are 296 slots; 162 CTAs (level 3)
+    // leave half of them empty and 332 CTAs (level 2) run a second, almost empty wave. Pick the S in {1,2,4} with the
+    // fewest (waves / S), i.e. the shortest critical path in units of whole-tile time.
+    const int slots = 2 * kNumSMs;
+    int best = 1;
+    double best_cost = (double)div_up(ctas, slots);
+    for (int cand = 2; cand <= std::min(4, g_tc_maxsplit); cand *= 2) {
+      if (K * nkc / cand < 4) break;
+      const double cost = (double)div_up(ctas * cand, slots) / cand;
+      if (cost < best_cost * 0.9) { best = cand; best_cost = cost; }
+    }
+    S = best;
   }
   p.ksplit = S;
   size_t smem = bstage * p.nbstages + map_bytes + 1024;
