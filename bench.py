@@ -358,9 +358,9 @@ def main():
                     scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                     config=dict(workload='ScanNet-shape synthetic scan (~150k pts, 18 classes), full SoftGroup '
                                 'inference, one scan per GPU per step', points=N_POINTS,
-                                model='SoftGroup 32ch x 7 blocks (softgroup_scannet.yaml), random init; point-wise head '
-                                'outputs are computed, then overwritten by synthetic predictions (one-hot*8+N(0,1), '
-                                'centroid offsets+N(0,3cm)) so grouping sees a trained-checkpoint load',
+                                path='softgroup_scannet.yaml hyper-parameters (32 channels x 7 U-Net levels), random-init '
+                                'weights; point-wise head outputs are computed, then overwritten by synthetic predictions '
+                                '(one-hot*8+N(0,1), centroid offsets+N(0,3cm)) so grouping sees a trained-checkpoint load',
                                 l2='flushed: 512 MiB memset between timed steps',
                                 parallelism='dp%d (independent scans, no data-path collective)' % world,
                                 proposals=int(out['proposals_offset'].numel() - 1),
