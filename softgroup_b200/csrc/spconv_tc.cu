@@ -57,28 +57,34 @@ struct TcArgs {
   int in_packed;   // input rows are already activated + split: per 32-channel chunk [16 words hi pairs | 16 words lo pairs]
   long long *dbg;  // optional timeline buffer (test hook)
   int skip;        // test hook (timing decomposition only, results are garbage): 1 no tcgen05.st, 2 no MMA, 4 no gather, 8 no weight copy
+  int gather_off;  // GATHER = 1: byte offset of the per-warp gather tiles (8 warps x 2 x 4 KB) in dynamic shared memory
 };
 
 // Warp roles: warps 0-3 = producer group 0, warps 4-7 = producer group 1 (one output row per thread; group g fills slot g
 // of every iteration pair), warp 8 = MMA issuer (warp-uniform, one elected lane), warp 9 = weight loader (TMA bulk copies).
 // Barriers per pair stage: full (8 producer-warp arrivals), bfull (weights: expect_tx), free (tcgen05.commit);
 // bars[8]: accumulator complete.
+// GATHER = 0: every producer lane fetches its own row slice (validated path). GATHER = 1 (round-2 candidate, packed
+// inputs only): lanes cooperate on rows through shared memory, see the producer branch.
+template <int GATHER>
 __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bars[12];  // [0..2] A full, [3..5] pair free, [8] done, [9..11] weights full
   __shared__ uint32_t s_tmem;
-  __shared__ long long s_dbg[64 * 8];  // in-kernel timeline (test hook): shared memory so that the stamps do not add global stores to the fences
+  __shared__ long long s_dbg[GATHER ? 8 : 64 * 8];  // in-kernel timeline (test hook): shared memory so that the stamps do not add global stores to the fences
   __shared__ unsigned int s_mask;
   __shared__ int s_list[32];
   __shared__ int s_nact;
-  __shared__ __align__(16) float s_scale[512], s_shift[512];
+  __shared__ __align__(16) float s_scale[GATHER ? 4 : 512], s_shift[GATHER ? 4 : 512];  // raw inputs never use GATHER = 1
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform copy for the role dispatch
   const bool mark_on = p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
   if (mark_on) p.dbg[64 * 8 + 0] = clock64();
-  if (p.dbg && (p.skip & 32))
-    for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) s_dbg[i] = 0;
+  if constexpr (GATHER == 0) {
+    if (p.dbg && (p.skip & 32))
+      for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) s_dbg[i] = 0;
+  }
   const bool producer = warp < 8;
   const int grp = warp >> 2;          // producer group (0/1)
   const int r = tid & (TC_ROWS - 1);  // row of this producer thread
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   const uint32_t tmem = s_tmem;
   if (mark_on) p.dbg[64 * 8 + 1] = clock64();
 
-  if (has_act) {
+  if (GATHER == 0 && has_act) {
     for (int c = tid; c < 512; c += TC_THREADS) {
       s_scale[c] = (c < p.Cin) ? __ldg(&p.in_scale[c]) : 0.f;
       s_shift[c] = (c < p.Cin) ? __ldg(&p.in_shift[c]) : 0.f;
@@ -179,6 +185,67 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
   const int npairs = (total + 1) >> 1;
   const int NP = NS >> 1;
   if (producer && p.in_packed) {
+   if constexpr (GATHER == 1) {
+    // ---- cooperative gather (packed inputs): the 8 lanes of a quarter-warp fetch one whole 128-byte row slice with
+    //      cp.async (16 B each), so a warp-wide copy touches 4 lines instead of 32 -- the per-lane gather of GATHER = 0 is
+    //      bound by L1 tag look-ups. Rows land in a per-warp shared-memory tile with the 16-byte chunk index XOR-ed
+    //      by (row & 7): both the quarter-warp writes and the lane-owns-a-row reads (LDS.128) are bank-conflict free.
+    //      Two tiles per warp: the copy of own iteration +1 is in flight while the current one moves to TMEM.
+    const uint32_t tile_u = smem_u32(smem + p.gather_off) + (uint32_t)warp * 8192u;
+    const int wrow0 = (warp & 3) * 32;  // first tile row of this warp (TMEM lanes wrow0 .. wrow0 + 31)
+    int ia = a0, ikc = k0 + grp;
+    while (ikc >= nkc) { ikc -= nkc; ia++; }
+    int nload = grp;
+    auto issue = [&](int b) {  // always commits one group (possibly empty) so that wait_group counts stay aligned
+      if (nload < total) {
+        const int o = s_list[ia];
+        const int i = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int R = 4 * j + (lane >> 3);
+          const int grow = row0 + wrow0 + R;
+          const int src = p.map ? map_s[o * TC_ROWS + wrow0 + R] : (grow < p.Mout ? grow : -1);
+          const uint32_t dst = tile_u + (uint32_t)b * 4096u + (uint32_t)(R * 128 + ((i ^ (R & 7)) << 4));
+          const float *g = p.in + (size_t)max(src, 0) * p.in_stride + p.in_off + ikc * TC_KC + i * 4;
+          const int nbytes = (src >= 0 && !(p.skip & 4)) ? 16 : 0;  // 0 source bytes = zero fill (absent neighbour)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(nbytes) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      nload += 2;
+      ikc += 2;
+      while (ikc >= nkc) { ikc -= nkc; ia++; }
+    };
+    int ps = 0, u = 0, b = 0;
+    issue(0);
+    issue(1);
+    for (int P = 0; P < npairs; P++) {
+      const bool work = 2 * P + grp < total;
+      if (u >= 1) mbar_wait(smem_u32(&bars[BAR_FREE + ps]), (uint32_t)((u - 1) & 1));
+      if (work) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group: tile b has landed
+        __syncwarp();
+        uint32_t w[32];
+        const uint32_t rbase = tile_u + (uint32_t)b * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w[4 * c + 0]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
+                       : "r"(rbase + (uint32_t)((c ^ (lane & 7)) << 4)));
+        __syncwarp();  // every lane has read its row before the tile is refilled
+        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.tmem_acols + (2 * ps + grp) * 32);
+        if (!(p.skip & 1)) tmem_st32(ta, w);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[BAR_FULL + ps]));
+      if (work) issue(b);  // own iteration +2 into the tile just drained (after the fence, like GATHER = 0)
+      b ^= 1;
+      if (++ps == NP) { ps = 0; u++; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+   } else {
     // ---- packed input (activated + split once by sgb_act_split): the gather is pure data movement, so the registers
     //      freed by the missing transform hold TWO future iterations of this thread's row (4 iterations ahead of the
     //      MMA warp counting both groups) -- the L2 latency of the gather is covered without shared memory.
@@ -242,6 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
       consume(va);
       if (j + 1 < npairs) consume(vb);
     }
+   }  // GATHER == 0
   } else if (producer) {
     float4 v[8];
     int vsrc = -1;
@@ -413,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
     int ps = 0, kc = k0_u;
     uint32_t par = 0u;
     for (int P = 0; P < npairs_u; P++) {
-      const bool dbg_on = p.dbg && (p.skip & 32) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && P < 64 && leader;
+      const bool dbg_on = GATHER == 0 && p.dbg && (p.skip & 32) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && P < 64 && leader;
       if (dbg_on) s_dbg[P * 8 + 4] = clock64();
       mbar_wait(bars_u + 8u * (uint32_t)(BAR_BFULL + ps), par);
       if (dbg_on) s_dbg[P * 8 + 5] = clock64();
@@ -566,8 +634,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) spconv_tc_kernel(TcArgs p) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
   }
   if (mark_on) p.dbg[64 * 8 + 7] = clock64();
-  if (mark_on && (p.skip & 32))
-    for (int i = 0; i < 64 * 8; i++) p.dbg[i] = s_dbg[i];
+  if constexpr (GATHER == 0) {
+    if (mark_on && (p.skip & 32))
+      for (int i = 0; i < 64 * 8; i++) p.dbg[i] = s_dbg[i];
+  }
 }
 
 }  // namespace sgb
@@ -604,13 +674,14 @@ __global__ void act_split_kernel(const float *__restrict__ x, int x_stride, int 
 }  // namespace sgb
 
 static long long *g_tc_dbg = nullptr;
-static int g_tc_prefetch = 0, g_tc_maxb = 3, g_tc_maxsplit = 8, g_tc_skip = 0, g_tc_split_policy = 0;
+static int g_tc_prefetch = 0, g_tc_maxb = 3, g_tc_maxsplit = 8, g_tc_skip = 0, g_tc_split_policy = 0, g_tc_gather = 0;
 
 extern "C" {
 
 void sgb_test_set_tc_debug(long long *d_buf) { g_tc_dbg = d_buf; }
 void sgb_test_set_tc_skip(int mask) { g_tc_skip = mask; }
-void sgb_test_set_tc_split_policy(int policy) { g_tc_split_policy = policy; }  // 0: validated heuristic, 1: wave-aware
+void sgb_test_set_tc_split_policy(int policy) { g_tc_split_policy = policy; }
+void sgb_test_set_tc_gather(int mode) { g_tc_gather = mode; }  // 0: per-lane gather (validated), 1: cooperative gather  // 0: validated heuristic, 1: wave-aware
 // test/bench hook: weight prefetch on/off, most pair stages in the ring (1..3), largest split-K cluster (1 = off)
 void sgb_test_set_tc_tuning(int prefetch, int max_pairs, int max_ksplit) {
   g_tc_prefetch = prefetch;
@@ -716,15 +787,24 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
   }
   p.ksplit = S;
   size_t smem = bstage * p.nbstages + map_bytes + 1024;
+  const bool coop = g_tc_gather == 1 && in_packed;  // round-2 candidate: cooperative gather through shared memory
+  p.gather_off = 0;
+  if (coop) {
+    p.gather_off = (int)align_up(bstage * p.nbstages + map_bytes);
+    smem = (size_t)p.gather_off + 8 * 8192 + 1024;
+  }
+  void (*kern)(TcArgs) = coop ? spconv_tc_kernel<1> : spconv_tc_kernel<0>;
   static bool attr_set = false;
   if (!attr_set) {
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid(tiles, div_up(N, NT), S);
   if (S == 1) {
-    spconv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -738,7 +818,7 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
     attr[0].val.clusterDim.z = S;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SGB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spconv_tc_kernel, p));
+    SGB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   }
   SGB_LAUNCH_CHECK();
   return SGB_OK;

@@ -199,3 +199,32 @@ def test_frontier_label_iteration_reaches_reference_labels(seed):
         if not any_push:
             break
     assert label == want
+
+
+# ---- cooperative gather of spconv_tc_kernel<1> (round-2 candidate): index arithmetic emulated lane by lane --------
+def test_coop_gather_tile_indexing_is_a_conflict_free_transpose():
+    """Write side: instruction j, lane l -> row R = 4j + (l >> 3), logical 16-byte chunk i = l & 7, physical chunk
+    i ^ (R & 7). Read side: lane r, register group c <- physical chunk c ^ (r & 7) of row r. Every lane must end up with
+    its own row in logical chunk order, and every quarter-warp access must touch 8 different 16-byte bank groups."""
+    rng = np.random.RandomState(0)
+    rows = rng.randint(0, 1000, (32, 8))  # rows[r][i] = id of logical chunk i of the source row feeding tile row r
+    tile = -np.ones((32, 8), np.int64)
+    for j in range(8):
+        for q in range(4):  # quarter-warp = one shared-memory wavefront of a 128-bit access
+            banks = set()
+            for l in range(8 * q, 8 * q + 8):
+                R, i = 4 * j + (l >> 3), l & 7
+                phys = i ^ (R & 7)
+                assert tile[R, phys] == -1
+                tile[R, phys] = rows[R, i]
+                banks.add((R * 128 + phys * 16) // 16 % 8)
+            assert len(banks) == 8
+    assert (tile >= 0).all()
+    for c in range(8):
+        for q in range(4):
+            banks = set()
+            for r in range(8 * q, 8 * q + 8):
+                phys = c ^ (r & 7)
+                assert tile[r, phys] == rows[r, c]  # register group c of lane r = logical chunk c of row r
+                banks.add((r * 128 + phys * 16) // 16 % 8)
+            assert len(banks) == 8
