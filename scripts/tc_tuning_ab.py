@@ -79,8 +79,7 @@ for tag, kw in [('bfs frontier labelling', dict(bfs_mode=1)), ('wave-aware split
     out = run(tag, 0, 3, 8)
     for k in ('proposals_idx', 'proposals_offset'):
         assert torch.equal(out[k], ref[k]), (tag, k)  # grouping is bit-exact by construction
-    for k in ('semantic_preds', 'pt_offsets'):
-        if k in out and k in ref:
-            d = (out[k].float() - ref[k].float()).abs().max().item()
-            print('   max |d %s| = %.3g' % (k, d))
+    # the instance head's scores go through the backbone features and the tiny U-Net: they see every conv variant
+    d = (out['device_instances']['score'] - ref['device_instances']['score']).abs().max().item()
+    print('   max |d instance score| = %.3g (scale %.3g)' % (d, ref['device_instances']['score'].abs().max().item()))
 knobs()
