@@ -80,6 +80,14 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        # development switches for candidates that are OFF by default (ROUND2_NOTES.md); the validated configuration is
+        # the one with none of these variables set
+        for env, setter in (('SGB_TC_GATHER', 'sgb_test_set_tc_gather'), ('SGB_TC_SPLIT_POLICY', 'sgb_test_set_tc_split_policy'),
+                            ('SGB_BFS_MODE', 'sgb_test_set_bfs_mode')):
+            if os.environ.get(env):
+                f = getattr(L, setter)
+                f.restype, f.argtypes = None, [ctypes.c_int]
+                f(int(os.environ[env]))
         _lib = L
     return _lib
 
