@@ -86,8 +86,11 @@ int sgb_voxelize_bp(const float *d_d_out, float *d_d_feats, const int32_t *d_rul
  * exactly like the reference (:55-61) and the caller relaunches with a larger meanActive
  * (softgroup/ops/functions.py:258-266). d_start_len int32 [n,2] = (start, count).
  * Returns (blocking) the total neighbour count, like the reference's `return cumsum`.
- * The *_async form leaves the total in d_total (int32 device scalar) and does not synchronise.
- * B must be <= 1023 and |xyz/radius| < 131072 (SGB_ERR_RANGE otherwise).
+ * The *_async form never synchronises: it leaves d_total[0] = total, d_total[1] = range-error flag (int32 [2], device).
+ * Points with a NaN / Inf coordinate get the empty list and are nobody's neighbour -- the reference's result, every
+ * comparison with them being false (:38-44). B must be <= 1023 and finite |xyz/radius| < 131070: SGB_ERR_RANGE
+ * otherwise (blocking form), or the flag in d_total[1] (async form; sgb_bfs_cluster_count reports it).
+ * capacity must stay below 2^31 entries (int32 cursor).
  * ------------------------------------------------------------------------------------------- */
 size_t sgb_ballquery_workspace_bytes(int n);
 long long sgb_ballquery_batch_p(int n, int meanActive, float radius, const float *d_xyz, const int32_t *d_batch_idxs,
@@ -122,12 +125,14 @@ long long sgb_octree_ball_query(const float *d_points, const float *d_boxes, con
  *   fill: d_cluster_idxs int32 [sumNPoint,2] (cluster id, point idx), d_cluster_offsets int32 [nCluster+1].
  * Optional per-node segments (d_node_seg int32 [N], d_seg_thr f32 [nSeg]) give every node the threshold of
  * its segment (used to cluster all classes of a scan in one call); pass NULL for a single threshold.
- * symmetric_hint != 0 promises that the list graph is symmetric (true for un-capped ball-query lists) and
- * enables the single-pass union-find labelling; 0 is always exact.
+ * The labelling is the exact directed one (lists cut by the 1000 cap make the graph asymmetric); label passes are
+ * enqueued in batches and the host waits ONCE, for the totals. d_upstream_err (nullable): device int32 error flag of
+ * the asynchronous ball query that produced the lists (d_total + 1 of sgb_ballquery_batch_p_async); it is read at that
+ * same wait and reported as SGB_ERR_RANGE.
  * ------------------------------------------------------------------------------------------- */
 size_t sgb_bfs_cluster_workspace_bytes(int N);
 int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, float thr,
-                          const int32_t *d_node_seg, const float *d_seg_thr, int symmetric_hint, void *d_ws,
+                          const int32_t *d_node_seg, const float *d_seg_thr, const int32_t *d_upstream_err, void *d_ws,
                           size_t ws_bytes, int *h_sumNPoint, int *h_maxLen, void *stream);
 /* scratch for fill: one bitmap row of ceil(maxLen/32) words per emitted point (0 when maxLen > 2048: fallback path) */
 size_t sgb_bfs_cluster_scratch_bytes(int sumNPoint, int maxLen);

@@ -72,18 +72,27 @@ __device__ __forceinline__ unsigned long long cell_key(int seg, int cx, int cy, 
          ((unsigned long long)(cy + kCellBias) << 18) | (unsigned long long)(cz + kCellBias);
 }
 
+// A point that is not hashed (NaN / Inf coordinate, or outside the addressable cell range) gets the empty list
+// start_len = (0, 0) here and is never a candidate of anybody else. For NaN / Inf that IS the reference's result:
+// every distance to or from such a point is NaN or +Inf, so `d2 < r2` never holds, not even with itself
+// (bfs_cluster.cu:38-44). A finite coordinate beyond +-131070 cells, or a segment id outside [0, 1023], is a limit of
+// this implementation: it raises the error flag scalars[2], reported as SGB_ERR_RANGE at the caller's next sync.
 __global__ void bq_insert_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ batch_idxs, int n,
-                                 double inv_h, BqWs w) {
+                                 double inv_h, int32_t *__restrict__ start_len, BqWs w) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double fx = floor((double)xyz[3 * (size_t)i] * inv_h);
-  double fy = floor((double)xyz[3 * (size_t)i + 1] * inv_h);
-  double fz = floor((double)xyz[3 * (size_t)i + 2] * inv_h);
+  const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+  double fx = floor((double)x * inv_h);
+  double fy = floor((double)y * inv_h);
+  double fz = floor((double)z * inv_h);
   int seg = batch_idxs[i];
   const double lim = (double)(kCellBias - 2);
   if (!(fabs(fx) < lim && fabs(fy) < lim && fabs(fz) < lim) || seg < 0 || seg > kMaxSeg) {
-    w.scalars[2] = 1;
+    const bool nonfinite = !(isfinite(x) && isfinite(y) && isfinite(z));
+    if (!nonfinite || seg < 0 || seg > kMaxSeg) w.scalars[2] = 1;
     w.slot_of[i] = -1;
+    start_len[2 * (size_t)i] = 0;
+    start_len[2 * (size_t)i + 1] = 0;
     return;
   }
   unsigned long long key = cell_key(seg, (int)fx, (int)fy, (int)fz);
@@ -401,7 +410,7 @@ static int bq_launch(int n, long long capacity, float radius, const float *xyz, 
   SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 64 * 4, st));
   double h = (double)radius * (1.0 + 1e-4);
   int nb = div_up(n, 256);
-  bq_insert_kernel<<<nb, 256, 0, st>>>(xyz, batch_idxs, n, 1.0 / h, w);
+  bq_insert_kernel<<<nb, 256, 0, st>>>(xyz, batch_idxs, n, 1.0 / h, start_len, w);
   SGB_LAUNCH_CHECK();
   bq_cellcnt_kernel<<<nb, 256, 0, st>>>(n, w);
   SGB_LAUNCH_CHECK();
@@ -443,15 +452,21 @@ int sgb_ballquery_batch_p_async(int n, long long capacity, float radius, const f
                                 int32_t *d_start_len, int32_t *d_total, void *d_ws, size_t ws_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
-    if (d_total) SGB_CUDA_CHECK(cudaMemsetAsync(d_total, 0, 4, st));
+    if (d_total) SGB_CUDA_CHECK(cudaMemsetAsync(d_total, 0, 8, st));
     return SGB_OK;
   }
   SGB_REQUIRE(capacity == 0 || d_idx, SGB_ERR_ARG, "null idx");
+  SGB_REQUIRE(capacity < (1ll << 31), SGB_ERR_RANGE, "ballquery: capacity must stay below 2^31 entries (int32 cursor and start_len)");
   BqWs w;
   int rc = bq_launch(n, capacity, radius, d_xyz, d_batch_idxs, d_batch_offsets, B, d_idx, d_start_len, d_ws, ws_bytes,
                      st, w);
   if (rc) return rc;
-  if (d_total) SGB_CUDA_CHECK(cudaMemcpyAsync(d_total, &w.scalars[3], 4, cudaMemcpyDeviceToDevice, st));
+  // d_total[0] = sum of list lengths, d_total[1] = range-error flag (hand d_total + 1 to sgb_bfs_cluster_count, which
+  // reports it at its own synchronisation: this entry point never waits for the device)
+  if (d_total) {
+    SGB_CUDA_CHECK(cudaMemcpyAsync(d_total, &w.scalars[3], 4, cudaMemcpyDeviceToDevice, st));
+    SGB_CUDA_CHECK(cudaMemcpyAsync(d_total + 1, &w.scalars[2], 4, cudaMemcpyDeviceToDevice, st));
+  }
   return SGB_OK;
 }
 

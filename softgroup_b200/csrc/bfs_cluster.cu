@@ -61,41 +61,19 @@ __global__ void bfs_init_kernel(int N, BfsWs w) {
   w.size[v] = 0;
 }
 
-// one warp per source node; pushes the (chased) label of u to every listed v
-__global__ void bfs_propagate_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len, int N,
-                                     BfsWs w) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  int nwarps = (gridDim.x * blockDim.x) >> 5;
-  volatile int32_t *label = w.label;
-  bool changed = false;
-  for (int u = warp; u < N; u += nwarps) {
-    int lu = label[u];
-    while (true) {  // pointer jumping: an ancestor's label is an ancestor too
-      int l2 = label[lu];
-      if (l2 >= lu) break;
-      lu = l2;
-    }
-    if (lane == 0 && lu < label[u]) atomicMin(&w.label[u], lu);
-    int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
-    for (int j = lane; j < l; j += 32) {
-      int v = __ldg(&idxs[(size_t)s + j]);
-      if (label[v] > lu) {
-        int old = atomicMin(&w.label[v], lu);
-        changed |= (old > lu);
-      }
-    }
-  }
-  if (__any_sync(0xffffffffu, changed) && lane == 0) w.scalars[0] = 1;
-}
-
-// Round-2 candidate (off by default, sgb_test_set_bfs_mode(1)): same least fixed point, but a node re-reads its list
-// only when its (chased) label is lower than the one it pushed last time. `w.wins` (idle until the emit phase) keeps
-// the last pushed label. Every pass still chases every node's label (2-3 words per node); the 4 bytes per edge are
-// read once per CHANGE of the source label instead of once per pass. The pass in which nobody pushes ends the loop:
-// then label[v] <= pushed[u] <= label[u] for every edge u->v, which is the fixed point of the full iteration.
+// Label propagation, one warp per source node: the (pointer-chased) label of u is pushed to every listed v. A node
+// re-reads its list only when its chased label is lower than the one it pushed last time (`w.wins`, idle until the
+// emit phase, keeps the last pushed label): every pass chases every node's label (2-3 words per node) but the 4 bytes
+// per edge are read once per CHANGE of the source label instead of once per pass (measured round 2: 1.43 -> 0.86 ms of
+// labelling per 150k-point scan). The pass in which nobody pushes ends the iteration: then
+// label[v] <= pushed[u] <= label[u] for every edge u->v, which is the fixed point of the full iteration.
+// Passes are enqueued in batches without a host round trip: pass `it` raises flags[it] when it pushed anything and
+// returns at once when pass it-1 did not (the fixed point has been reached; the remaining launches of the batch are
+// empty). The host looks at the last flag of the batch at the sync it needs anyway for the cluster totals.
 __global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len,
-                                              int N, BfsWs w, int first_pass) {
+                                              int N, BfsWs w, int it, int cont, int32_t *__restrict__ flags) {
+  if (it > 0 && *(volatile int32_t *)&flags[it - 1] == 0) return;
+  const int first_pass = it == 0 && !cont;  // cont: a later batch continues the iteration (w.wins is valid)
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -103,7 +81,7 @@ __global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, 
   bool pushed_any = false;
   for (int u = warp; u < N; u += nwarps) {
     int lu = label[u];
-    while (true) {
+    while (true) {  // pointer jumping: an ancestor's label is an ancestor too
       int l2 = label[lu];
       if (l2 >= lu) break;
       lu = l2;
@@ -120,7 +98,7 @@ __global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, 
     __syncwarp();
     if (lane == 0) w.wins[u] = lu;
   }
-  if (pushed_any && lane == 0) w.scalars[0] = 1;
+  if (pushed_any && lane == 0) flags[it] = 1;
 }
 
 __global__ void bfs_size_kernel(int N, const int32_t *__restrict__ start_len, BfsWs w) {
@@ -440,11 +418,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
 
 using namespace sgb;
 
-static int g_bfs_mode = 0;  // 0: full propagation passes (validated), 1: frontier passes (round-2 candidate)
-
 extern "C" {
-
-void sgb_test_set_bfs_mode(int mode) { g_bfs_mode = mode; }
 
 size_t sgb_bfs_cluster_workspace_bytes(int N) {
   if (N < 0) N = 0;
@@ -455,10 +429,9 @@ size_t sgb_bfs_cluster_workspace_bytes(int N) {
 }
 
 int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_start_len, int N, float thr,
-                          const int32_t *d_node_seg, const float *d_seg_thr, int symmetric_hint, void *d_ws,
+                          const int32_t *d_node_seg, const float *d_seg_thr, const int32_t *d_upstream_err, void *d_ws,
                           size_t ws_bytes, int *h_sumNPoint, int *h_maxLen, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  (void)symmetric_hint;
   SGB_REQUIRE(N >= 0 && h_sumNPoint, SGB_ERR_ARG, "bfs_cluster arguments");
   if (h_maxLen) *h_maxLen = 0;
   if (N == 0) { *h_sumNPoint = 0; return 0; }
@@ -471,29 +444,35 @@ int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_sta
   bfs_init_kernel<<<nb, 256, 0, st>>>(N, w);
   SGB_LAUNCH_CHECK();
   int grid = std::min(div_up((long long)N * 32, 256), kNumSMs * 16);
-  for (int it = 0; it < 100000; it++) {
-    SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 4, st));
-    if (g_bfs_mode == 1)
-      bfs_propagate_frontier_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w, it == 0);
-    else
-      bfs_propagate_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w);
-    SGB_LAUNCH_CHECK();
-    int changed = 0;
-    SGB_CUDA_CHECK(cudaMemcpyAsync(&changed, w.scalars, 4, cudaMemcpyDeviceToHost, st));
-    SGB_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (!changed) break;
-  }
-  bfs_size_kernel<<<nb, 256, 0, st>>>(N, d_start_len, w);
-  SGB_LAUNCH_CHECK();
-  bfs_pack_kernel<<<nb, 256, 0, st>>>(N, thr, d_node_seg, d_seg_thr, w);
-  SGB_LAUNCH_CHECK();
-  int rc = exclusive_scan_i64(w.packed, w.packed, (size_t)N, w.totals, w.scan_tmp, st);
-  if (rc) return rc;
+  // passes in batches of kBatch launches, ONE host synchronisation per batch (the one that reads the cluster totals):
+  // sizes / threshold / scan are enqueued optimistically behind the batch and redone in the rare case that the last
+  // pass of the batch still pushed labels (flags live in scalars[8..8+kBatch)).
+  constexpr int kBatch = 12;
+  int32_t *flags = w.scalars + 8;
   long long tot = 0;
-  int sc[4];
-  SGB_CUDA_CHECK(cudaMemcpyAsync(&tot, w.totals, 8, cudaMemcpyDeviceToHost, st));
-  SGB_CUDA_CHECK(cudaMemcpyAsync(sc, w.scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
-  SGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  int sc[8 + kBatch], up_err = 0;
+  for (int batch = 0; batch < 100000; batch++) {
+    if (batch > 0) {
+      SGB_CUDA_CHECK(cudaMemsetAsync(flags, 0, kBatch * 4, st));
+      SGB_CUDA_CHECK(cudaMemsetAsync(w.size, 0, (size_t)N * 4, st));
+    }
+    for (int it = 0; it < kBatch; it++) {
+      bfs_propagate_frontier_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w, it, batch > 0, flags);
+      SGB_LAUNCH_CHECK();
+    }
+    bfs_size_kernel<<<nb, 256, 0, st>>>(N, d_start_len, w);
+    SGB_LAUNCH_CHECK();
+    bfs_pack_kernel<<<nb, 256, 0, st>>>(N, thr, d_node_seg, d_seg_thr, w);
+    SGB_LAUNCH_CHECK();
+    int rc = exclusive_scan_i64(w.packed, w.packed, (size_t)N, w.totals, w.scan_tmp, st);
+    if (rc) return rc;
+    SGB_CUDA_CHECK(cudaMemcpyAsync(&tot, w.totals, 8, cudaMemcpyDeviceToHost, st));
+    SGB_CUDA_CHECK(cudaMemcpyAsync(sc, w.scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    if (d_upstream_err && batch == 0) SGB_CUDA_CHECK(cudaMemcpyAsync(&up_err, d_upstream_err, 4, cudaMemcpyDeviceToHost, st));
+    SGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    SGB_REQUIRE(up_err == 0, SGB_ERR_RANGE, "ball query upstream of bfs_cluster: |xyz/radius| >= 131070 or segment id outside [0,1023]");
+    if (sc[8 + kBatch - 1] == 0) break;  // the last pass of the batch pushed nothing: fixed point
+  }
   if (h_maxLen) *h_maxLen = sc[1];
   *h_sumNPoint = (int)(tot & 0xFFFFFFFFll);
   return (int)(tot >> 32);

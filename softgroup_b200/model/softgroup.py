@@ -375,9 +375,9 @@ class SoftGroup(nn.Module):
         thr_c = torch.tensor([npoint_thr if cnm[c] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[c]))
                               for c in classes], dtype=torch.float32, device=dev)
         seg_thr = thr_c.repeat_interleave(batch_size).contiguous()
-        capped = False  # lists that hit the 1000 cap make the graph asymmetric -> exact directed labelling
+        # lists that hit the 1000 cap make the graph asymmetric: the labelling is the exact directed one
         cidx, coff = bfs_cluster_segments(neighbor_inds, start_len, 0.0, node_seg=seg, seg_thr=seg_thr,
-                                          symmetric=not capped, nactive=n_active)
+                                          nactive=n_active[0:1], upstream_err=n_active[1:2])
         if cidx.size(0) == 0:
             return empty
         # proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1]] (:464)

@@ -35,7 +35,7 @@ SIGNATURES = {
     'sgb_octree_build': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     'sgb_octree_ball_query': (c_longlong, [_P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P]),
     'sgb_bfs_cluster_workspace_bytes': (c_size_t, [c_int]),
-    'sgb_bfs_cluster_count': (c_int, [_P, _P, c_int, c_float, _P, _P, c_int, _P, c_size_t, _INTP, _INTP, _P]),
+    'sgb_bfs_cluster_count': (c_int, [_P, _P, c_int, c_float, _P, _P, _P, _P, c_size_t, _INTP, _INTP, _P]),
     'sgb_bfs_cluster_scratch_bytes': (c_size_t, [c_int, c_int]),
     'sgb_bfs_cluster_fill': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P, c_size_t, _P]),
     'sgb_sec_mean': (c_int, [_P, _P, _P, c_int, c_int, _P]),
@@ -80,14 +80,6 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        # development switches for candidates that are OFF by default (ROUND2_NOTES.md); the validated configuration is
-        # the one with none of these variables set
-        for env, setter in (('SGB_TC_GATHER', 'sgb_test_set_tc_gather'), ('SGB_TC_SPLIT_POLICY', 'sgb_test_set_tc_split_policy'),
-                            ('SGB_BFS_MODE', 'sgb_test_set_bfs_mode')):
-            if os.environ.get(env):
-                f = getattr(L, setter)
-                f.restype, f.argtypes = None, [ctypes.c_int]
-                f(int(os.environ[env]))
         _lib = L
     return _lib
 

@@ -137,22 +137,25 @@ ballquery_batch_p = BallQueryBatchP.apply
 def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
     """Device-resident variant for the fused forward: the index buffer is sized for the cap (n * 1000 entries, only
     the used prefix is ever touched), so there is no overflow relaunch (functions.py:258-266 of the reference) and
-    no host synchronisation. Returns (idx buffer int32 [n*1000], start_len int32 [n,2], total int32 [1] on device);
-    only idx[start:start+len] per point is meaningful."""
+    no host synchronisation. Returns (idx buffer int32 [n*1000], start_len int32 [n,2], total int32 [2] on device:
+    [sum of list lengths, range-error flag]); only idx[start:start+len] per point is meaningful. The error flag is
+    reported by the next bfs_cluster_segments(..., upstream_err=total[1:]) at its own synchronisation. The buffer is
+    4 KB per entry (0.5 GB at 131k entries, 3.2 GB at 800k): sized for 180 GB of HBM, int32 cursor => n < 2^31/1000."""
     n = coords.size(0)
     assert coords.is_contiguous() and coords.is_cuda
     L = _lib.lib()
     dev = coords.device
     B = batch_offsets.numel() - 1
     start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
-    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    total = torch.zeros(2, dtype=torch.int32, device=dev)
+    assert n * 1000 < 2**31, 'ballquery_batch_p_nosync: %d entries need an index buffer beyond the int32 cursor' % n
     cap = max(n, 1) * 1000
     idx = torch.empty(cap, dtype=torch.int32, device=dev)
     if n == 0:
         return idx, start_len, total
     ws = _ws(L.sgb_ballquery_workspace_bytes(n), dev)
     # algorithmic bytes need nActive, which stays on the device: resolved lazily when the profiler is summarised
-    with profiler.record('ballquery_batch_p', lambda: 24 * n + 4 * (B + 1) + 4 * int(total.item())):
+    with profiler.record('ballquery_batch_p', lambda: 24 * n + 4 * (B + 1) + 4 * int(total[0].item())):
         check(
             L.sgb_ballquery_batch_p_async(n, cap, float(radius), ptr(coords), ptr(batch_idxs), ptr(batch_offsets), B,
                                           ptr(idx), ptr(start_len), ptr(total), ptr(ws), ws.numel(), _stream()),
@@ -163,8 +166,8 @@ def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
 # ----------------------------------------------------------------------------------------------
 # clustering
 # ----------------------------------------------------------------------------------------------
-def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, symmetric=False,
-                         nactive=None):
+def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, nactive=None,
+                         upstream_err=None):
     """GPU clustering on device tensors. thr: float threshold on the component size (already multiplied by the
     class mean when that applies). Optional per-node segment thresholds. Returns CUDA tensors
     (cluster_idxs int32 [sumNPoint,2], cluster_offsets int32 [nCluster+1])."""
@@ -179,7 +182,7 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     with profiler.record('bfs_cluster(label)', lambda: 8 * N + 4 * nb()):
         nC = check(
             L.sgb_bfs_cluster_count(ptr(ball_query_idxs), ptr(start_len), N, float(thr), ptr(node_seg), ptr(seg_thr),
-                                    int(bool(symmetric)), ptr(ws), ws.numel(), ctypes.byref(s), ctypes.byref(mx),
+                                    ptr(upstream_err), ptr(ws), ws.numel(), ctypes.byref(s), ctypes.byref(mx),
                                     _stream()),
             'sgb_bfs_cluster_count')
     cluster_idxs = torch.empty((s.value, 2), dtype=torch.int32, device=dev)

@@ -1,7 +1,7 @@
-"""NOT COLLECTED YET (file name does not start with test_): the CUDA forward against the reference-generated fixture
-tests/golden/ref_forward_c1.npz. Written at the end of round 1 after the GPU budget was spent; first thing to run on
-the GPU in round 2 (`python -m pytest tests/pending_gpu_forward_golden.py -m gpu`), then rename to
-test_gpu_forward_golden.py once the tolerances below have been confirmed on hardware."""
+"""The CUDA forward against the reference-generated fixture tests/golden/ref_forward_c1.npz (the reference's own
+`forward_test`, softgroup/model/softgroup.py:300-361, run on CPU stand-ins by tests/golden/make_forward_golden.py):
+backbone + heads, then grouping / clusters_voxelization / tiny U-Net / instance heads from the fixture's
+intermediates. First run on a B200 in round 2 (2 passed)."""
 import os
 import sys
 

@@ -16,10 +16,10 @@ from softgroup_b200.model import softgroup as sg_module
 def _fake_ballquery_nosync(coords, batch_idxs, batch_offsets, radius):
     idx, sl = oracle.ballquery_batch_p(coords.numpy(), batch_idxs.numpy(), batch_offsets.numpy(), radius)
     return (torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(sl.astype(np.int32)),
-            torch.tensor([idx.size], dtype=torch.int32))
+            torch.tensor([idx.size, 0], dtype=torch.int32))
 
 
-def _fake_bfs_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, symmetric=False, nactive=None):
+def _fake_bfs_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, nactive=None, upstream_err=None):
     """bfs_cluster.cpp:33-126 over the whole node set with a per-seed-segment threshold (what the library computes)."""
     idxs, sl = ball_query_idxs.numpy(), start_len.numpy()
     n = sl.shape[0]
