@@ -80,6 +80,58 @@ def test_subm_conv_vs_oracle(Cin, Cout):
     assert 'k' in x.indice_dict
 
 
+def _surface_case(seed, n_rows, extent=200):
+    """Voxels on densely filled, gently warped plane patches (surface-like occupancy: ~9 of the 27 neighbours present,
+    the statistics of a scanned room), enough rows to fill the machine with whole 128-row tiles."""
+    rng = np.random.RandomState(seed)
+    pts, have = [], 0
+    while have < n_rows * 1.2:
+        axis = rng.randint(3)
+        c = rng.randint(10, extent - 10)
+        w, h = rng.randint(50, 120, 2)
+        u0, v0 = rng.randint(0, extent - w), rng.randint(0, extent - h)
+        u, v = np.meshgrid(np.arange(u0, u0 + w), np.arange(v0, v0 + h), indexing='ij')
+        u, v = u.ravel(), v.ravel()
+        wob = np.round(np.sin(u / 9.0) * 2 + np.cos(v / 7.0) * 2).astype(np.int64)
+        pts.append(np.insert(np.stack([u, v], 1), axis, c + wob, axis=1))
+        have += len(u)
+    idx = np.unique(np.concatenate(pts, 0), axis=0)
+    idx = idx[rng.permutation(len(idx))][:n_rows]
+    idx = np.concatenate([np.zeros((len(idx), 1), np.int64), idx], 1).astype(np.int32)
+    return idx
+
+
+def _rel_elem(got, want):
+    """north star wording: float features within 1e-4 RELATIVE -- per element, with an absolute floor of 1e-6 of the
+    tensor's largest magnitude for values that cancel to ~0: max over elements of |got-want| / (|want| + 1e-2 max|want|)
+    would hide errors on small elements, so the bound is |got - want| <= tol * |want| + 1e-6 * max|want|."""
+    floor = 1e-6 * np.abs(want).max()
+    return float((np.maximum(np.abs(got - want) - floor, 0) / np.maximum(np.abs(want), 1e-30)).max())
+
+
+@pytest.mark.parametrize('Cin,Cout,n_rows', [(32, 32, 40000), (64, 64, 24000), (96, 96, 24000), (128, 128, 20000),
+                                             (192, 96, 20000), (64, 32, 40000), (224, 224, 20000)])
+def test_subm_conv_bench_tile_configs_vs_oracle(Cin, Cout, n_rows):
+    """The tile configurations the 150k-point bench actually runs (>= 148 row tiles, so no column shrink / split-K of
+    the small cases above): compared with the float64-accumulating oracle PER ELEMENT at the north-star tolerance."""
+    idx = _surface_case(Cin * 7 + Cout, n_rows)
+    rng = np.random.RandomState(Cin + Cout)
+    feats = (rng.randn(len(idx), Cin) * rng.uniform(0.2, 3.0, size=(1, Cin))).astype(np.float32)
+    W = (rng.randn(Cout, 3, 3, 3, Cin) / np.sqrt(12 * Cin)).astype(np.float32)
+    scale, shift = rng.rand(Cin).astype(np.float32) + 0.5, rng.randn(Cin).astype(np.float32) * 0.3
+    mp = so.subm_map(idx)
+    assert (mp >= 0).sum(0).mean() > 5  # surface-like: several neighbours per row
+    M = len(idx)
+    assert M >= 148 * 128
+    wk = torch.from_numpy(W.reshape(Cout, 27, Cin).transpose(1, 2, 0).copy()).cuda()
+    out = spconv.conv_forward(_cuda(feats), Cin, 0, _cuda(mp), 27, M, wk, Cin, Cout, act=(_cuda(scale), _cuda(shift)))
+    act = np.maximum(feats * scale + shift, 0).astype(np.float32)
+    want = so.conv_from_map(act, mp, W, acc64=True)
+    got = out.cpu().numpy()
+    assert _rel(got, want) < TOL
+    assert _rel_elem(got, want) < 1e-4
+
+
 def test_conv_fused_act_residual_bias_strided():
     idx, feats, _, _ = _case(5, C=40)
     rng = np.random.RandomState(3)

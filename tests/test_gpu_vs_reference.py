@@ -56,6 +56,57 @@ def test_ballquery_vs_reference_kernel(ref, n, sigma, r):
         assert np.array_equal(R[i], O[i]), i   # oracle restatement == reference kernel (pins the oracle)
 
 
+def test_ballquery_nonfinite_points_vs_reference_kernel(ref):
+    """NaN / Inf coordinates (a diverged offset head): the reference kernel gives such a point the empty list and nobody
+    lists it, every comparison with it being false (bfs_cluster.cu:38-44). Same here, blocking AND asynchronous entry
+    points (round-1 advice: the async path left start_len rows of dropped points uninitialised); the clustering
+    downstream then sees isolated nodes."""
+    from softgroup_b200.ops import ballquery_batch_p_nosync, bfs_cluster_segments
+    rng = np.random.RandomState(7)
+    n = 3000
+    xyz = (rng.rand(4, 3)[rng.randint(0, 4, n)] + rng.randn(n, 3) * 0.02).astype(np.float32)
+    bad = rng.choice(n, 40, replace=False)
+    xyz[bad[:15], rng.randint(0, 3, 15)] = np.nan
+    xyz[bad[15:30], rng.randint(0, 3, 15)] = np.inf
+    xyz[bad[30:], rng.randint(0, 3, 10)] = -np.inf
+    bi = np.zeros(n, np.int32)
+    bo = np.array([0, n], np.int32)
+    ridx, rsl = _ref_ballquery(ref, _c(xyz), _c(bi), _c(bo), 0.04, 100)
+    gidx, gsl = ops.ballquery_batch_p(_c(xyz), _c(bi), _c(bo), 0.04, 100)
+    oidx, osl = oracle.ballquery_batch_p(xyz, bi, bo, 0.04)
+    R, G = _lists(ridx, rsl), _lists(gidx, gsl)
+    O = [oidx[s:s + l] for s, l in osl]
+    for i in range(n):
+        assert np.array_equal(R[i], G[i]), i
+        assert np.array_equal(R[i], O[i]), i
+    assert all(len(G[i]) == 0 for i in bad)
+    # asynchronous entry point used by the fused forward + clustering on its lists
+    aidx, asl, tot = ballquery_batch_p_nosync(_c(xyz), _c(bi), _c(bo), 0.04)
+    A = _lists(aidx, asl)
+    for i in range(n):
+        assert np.array_equal(A[i], O[i]), i
+    assert int(tot[0]) == oidx.size and int(tot[1]) == 0
+    cidx, coff = bfs_cluster_segments(aidx, asl, 10.0, nactive=tot[0:1], upstream_err=tot[1:2])
+    mean = np.full(20, -1, np.float32)
+    wi, wo = oracle.bfs_cluster(mean, oidx, osl, 10.0, 3)
+    assert np.array_equal(cidx.cpu().numpy(), wi) and np.array_equal(coff.cpu().numpy(), wo)
+
+
+def test_ballquery_out_of_range_is_reported():
+    """A finite coordinate beyond the addressable cell range is a limit of this implementation: SGB_ERR_RANGE from the
+    blocking call, and from the clustering call downstream of the asynchronous one (never silent garbage)."""
+    from softgroup_b200.ops import ballquery_batch_p_nosync, bfs_cluster_segments
+    from softgroup_b200.ops._lib import SgbError
+    xyz = np.random.RandomState(0).rand(500, 3).astype(np.float32)
+    xyz[17, 1] = 1e7
+    bi, bo = np.zeros(500, np.int32), np.array([0, 500], np.int32)
+    with pytest.raises(SgbError):
+        ops.ballquery_batch_p(_c(xyz), _c(bi), _c(bo), 0.04, 100)
+    aidx, asl, tot = ballquery_batch_p_nosync(_c(xyz), _c(bi), _c(bo), 0.04)
+    with pytest.raises(SgbError):
+        bfs_cluster_segments(aidx, asl, 10.0, nactive=tot[0:1], upstream_err=tot[1:2])
+
+
 def test_voxelize_fp_vs_reference_kernel(ref):
     rng = np.random.RandomState(1)
     coords = np.concatenate([np.zeros((20000, 1), np.int64), rng.randint(0, 30, (20000, 3))], 1)
