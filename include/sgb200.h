@@ -227,6 +227,30 @@ int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const in
 int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
                   float *d_y, int M, int C, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Round-2 sparse convolution (spconv_tma.cu): same contraction as sgb_spconv_forward_tc, input rows fetched by TMA row
+ * gather (cp.async.bulk.tensor ... tile::gather4) from PACKED activations, persistent CTAs, fused output packing.
+ * Packed rows: per 32-channel chunk 16 words of fp16 hi pairs then 16 words of fp16 lo pairs, x = hi + lo * 2^-shift with
+ * shift = sgb_spconv_lo_shift() (weights packed by the host with the same shift: [K][nkc][4][2][N][8 halves]).
+ *   d_in_pk [Min rows][in_stride words]; row index Min stands for "no neighbour" (out of bounds: read as zero).
+ *   outputs (either or both): d_out fp32 rows (strided like sgb_spconv_forward_tc); d_pk_out packed rows written at
+ *   channel offset pk_coff (multiple of 8) after y = relu?(x * pk_scale[c] + pk_shift[c]) per OUTPUT channel c -- the
+ *   consumer's BatchNorm(eval)+ReLU folded into this producer; pk_fill != 0 also zeroes the upper half of a last chunk
+ *   that N = Cout rounded to 16 leaves half written.
+ * sgb_act_pack: the same packing for tensors without a producing convolution (C real channels, zero up to Cfill).
+ * sgb_spconv_overflow: a packed value beyond the fp16 range (|y| > 65504, or NaN) raises a device flag instead of
+ * saturating silently; this call reads and clears it (blocking 4-byte read).
+ * ------------------------------------------------------------------------------------------- */
+int sgb_spconv_lo_shift(void);
+int sgb_spconv_overflow(int *h_flag, void *stream);
+int sgb_act_pack(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
+                 float *d_pk, int pk_stride, int pk_coff, int M, int C, int Cfill, void *stream);
+int sgb_spconv_forward_tma(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
+                           const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
+                           const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
+                           int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill,
+                           void *stream);
+
 /* y[i, c] = max(x[i, c]*scale[c] + shift[c], 0) (relu != 0) -- BatchNorm1d(eval)+ReLU over rows. */
 int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const float *d_shift, int relu, float *d_y,
                 int y_stride, int M, int C, void *stream);
@@ -241,6 +265,39 @@ int sgb_gather_rows(const float *d_in, const int32_t *d_index, float *d_out, int
  * (12 bytes per run + 2 always suffices). No CUDA involved. */
 long long sgb_rle_format_ids(const int32_t *h_ids, const long long *h_offs, int n_masks, char *h_out,
                              long long out_cap, long long *h_out_offs);
+
+/* ---------------------------------------------------------------------------------------------
+ * Instance masks, RLE, panoptic paste and evaluation intersections on the GPU (instances.cu) -- replace the dense
+ * [nProposal, N] masks + numpy RLE of get_instances (softgroup/model/softgroup.py:537-604, softgroup/util/rle.py:5-19),
+ * the numpy paste loop of panoptic_fusion (softgroup.py:606-639) and the per-pair np.count_nonzero of
+ * ScanNetEval.assign_instances_for_scan (softgroup/evaluation/instance_eval.py:262-293).
+ * Masks are bitmaps [rows][W], W = sgb_bitmap_words(N) = ceil((N+1)/32) 32-bit words (bit N always 0).
+ *   sgb_inst_count:   npoint[p*nI+i] = #entries of proposal p with mask_scores[e,i] > thr (zeroed here).
+ *   sgb_inst_scatter: bitmaps (zeroed here) of the kept instances; slot int32 [nI*nP], class-major (i*nP+p): bitmap row or -1.
+ *   sgb_bitmap_set:   generic (row, point) -> bit; clear != 0 zeroes the bitmaps first.
+ *   sgb_rle_count (blocking) / sgb_rle_fill: 1-based transition positions of every mask, ascending = `runs` of rle.py:15
+ *     before `runs[1::2] -= runs[::2]`; inst_off int32 [n_inst+1]. sgb_rle_format_runs (host): the `counts` strings.
+ *   sgb_bitmap_intersections: inter[r*nG+g], vert[r], void[r] from gslot int32 [N] (>= 0: gt column, -2: void, -1: other).
+ *   sgb_panoptic_paste: instances visited in d_order; skipped when intersect/(size+1e-5) > skip_iou (float64), else
+ *     pasted where nothing was pasted before: pan_cls[pt] = d_cls[row], pan_ids[pt] = 1, 2, ... in paste order.
+ * ------------------------------------------------------------------------------------------- */
+int sgb_inst_count(const int32_t *d_proposals_idx, const float *d_mask_scores, int ms_stride, int S, int nI, float thr,
+                   int32_t *d_npoint, int nP, void *stream);
+size_t sgb_bitmap_words(int N);
+int sgb_inst_scatter(const int32_t *d_proposals_idx, const float *d_mask_scores, int ms_stride, int S, int nI, int nP, float thr,
+                     const int32_t *d_slot, uint32_t *d_bitmaps, int n_inst, int N, void *stream);
+int sgb_bitmap_set(const int32_t *d_row, const int32_t *d_pt, long long n, uint32_t *d_bitmaps, int n_rows, int N, int clear,
+                   void *stream);
+size_t sgb_rle_workspace_bytes(int n_inst, int N);
+long long sgb_rle_count(const uint32_t *d_bitmaps, int n_inst, int N, void *d_ws, size_t ws_bytes, void *stream);
+int sgb_rle_fill(const uint32_t *d_bitmaps, int n_inst, int N, int total_trans, int32_t *d_trans, int32_t *d_inst_off, void *d_ws,
+                 size_t ws_bytes, void *stream);
+long long sgb_rle_format_runs(const int32_t *h_trans, const int32_t *h_offs, int n_masks, char *h_out, long long out_cap,
+                              long long *h_out_offs);
+int sgb_bitmap_intersections(const uint32_t *d_bitmaps, int n_rows, int N, const int32_t *d_gslot, int nG, int32_t *d_inter,
+                             int32_t *d_vert, int32_t *d_void, void *stream);
+int sgb_panoptic_paste(const uint32_t *d_bitmaps, int N, const int32_t *d_order, const int32_t *d_cls, int n_inst, double skip_iou,
+                       uint32_t *d_prev, uint32_t *d_pan_cls, uint32_t *d_pan_ids, void *stream);
 
 #ifdef __cplusplus
 }

@@ -87,3 +87,37 @@ def install(name='softgroup.ops'):
     """Register under the name the reference imports (`from ..ops import ...`, softgroup/model/softgroup.py:11-13)."""
     sys.modules[name] = sys.modules[__name__]
     return sys.modules[__name__]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Dense stand-ins for softgroup_b200.ops.instances (the GPU bitmap path of get_instances): exactly the reference's
+# dense-mask steps, softgroup/model/softgroup.py:551-580 and softgroup/util/rle.py:5-19. CPU tests only.
+# ---------------------------------------------------------------------------------------------------------------------
+def instance_point_counts(proposals_idx, mask_scores, n_classes, thr, n_proposals):
+    pidx, ms = _n(proposals_idx), _n(mask_scores)
+    out = np.zeros((n_proposals, n_classes), np.int32)
+    for i in range(n_classes):
+        on = ms[:, i] > thr
+        np.add.at(out[:, i], pidx[on, 0], 1)  # (proposal, point) pairs are unique: == mask_pred.sum(1) (:563-565)
+    return _t(out)
+
+
+def instance_bitmaps(proposals_idx, mask_scores, n_classes, thr, keep, n_points):
+    """'bitmaps' are dense uint8 masks [n_inst, n_points] here (:553-555 `mask_pred[proposals_idx[...]] = 1`)."""
+    pidx, ms, kp_ = _n(proposals_idx), _n(mask_scores), _n(keep)
+    kc, kp = np.nonzero(kp_.T)
+    masks = np.zeros((kc.size, int(n_points)), np.uint8)
+    for k, (i, p) in enumerate(zip(kc, kp)):
+        sel = (pidx[:, 0] == p) & (ms[:, i] > thr)
+        masks[k, pidx[sel, 1]] = 1
+    return _t(masks), _t(kc.astype(np.int64)), _t(kp.astype(np.int64))
+
+
+def bitmaps_to_rle(masks, n_points):
+    out = []
+    for m in _n(masks):
+        m = np.concatenate([[0], m, [0]])  # rle.py:13-17
+        runs = np.where(m[1:] != m[:-1])[0] + 1
+        runs[1::2] -= runs[::2]
+        out.append(dict(length=int(n_points), counts=' '.join(str(x) for x in runs)))
+    return out

@@ -210,6 +210,82 @@ __global__ void __launch_bounds__(192) stream_kernel(const __grid_constant__ CUt
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// D. issue-cost variants. mode 0: every gather4 issued from warp-uniform operands (row ids broadcast with __shfl_sync,
+//    unrolled: no ELECT/R2UR.BROADCAST/BRA.U.ANY waterfall per lane); mode 1: cp.async 16 B x 8 lanes per row written
+//    straight into the SWIZZLE_128B positions (4 rows per warp instruction), completion by cp.async.mbarrier.arrive.
+//    P producer warps, warp P consumes.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(544) stream2_kernel(const __grid_constant__ CUtensorMap tm, const uint32_t *__restrict__ table, int rowwords,
+                                                      int nrows, const int *__restrict__ idx, int iters_total, int S, int P, int ncol) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long full[16], empty[16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(smem_u32(&full[s]), MODE == 0 ? P : P * 32); mbar_init(smem_u32(&empty[s]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int per = 32 / P;  // row quads per warp per stage
+  const uint32_t base = smem_u32(smem);
+  if (warp < P) {
+    int s = 0, u = 0, n = 0;
+    for (int it = blockIdx.x; it < iters_total; it += gridDim.x, n++) {
+      const int col = (n % ncol) * 32;
+      if (MODE == 0) {
+        // lane j < per keeps the 4 row ids of quad warp*per + j
+        int4 cur = make_int4(0, 0, 0, 0);
+        if (lane < per) cur = __ldg(reinterpret_cast<const int4 *>(idx + (size_t)it * 128) + warp * per + lane);
+        if (u >= 1) mbar_wait(smem_u32(&empty[s]), (uint32_t)((u - 1) & 1));
+        const uint32_t bar = smem_u32(&full[s]);
+        if (lane == 0) mbar_expect(bar, (uint32_t)per * 512u);
+        __syncwarp();
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+#pragma unroll 8
+        for (int j = 0; j < per; j++) {
+          const int r0 = __shfl_sync(0xffffffffu, cur.x, j), r1 = __shfl_sync(0xffffffffu, cur.y, j);
+          const int r2 = __shfl_sync(0xffffffffu, cur.z, j), r3 = __shfl_sync(0xffffffffu, cur.w, j);
+          const uint32_t dst = base + (uint32_t)s * 16384u + (uint32_t)(warp * per + j) * 512u;
+          if (leader) gather4(dst, &tm, col, r0, r1, r2, r3, bar);
+        }
+      } else {
+        int rid[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) rid[j] = (j < per) ? __ldg(idx + (size_t)it * 128 + (warp * per + j) * 4 + (lane >> 3)) : 0;
+        if (u >= 1) mbar_wait(smem_u32(&empty[s]), (uint32_t)((u - 1) & 1));
+        const uint32_t bar = smem_u32(&full[s]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (j < per) {
+            const int row = (warp * per + j) * 4 + (lane >> 3);
+            const int ch = lane & 7;
+            const uint32_t dst = base + (uint32_t)s * 16384u + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+            const bool ok = rid[j] >= 0 && rid[j] < nrows;
+            const uint32_t *g = table + (size_t)(ok ? rid[j] : 0) * rowwords + col + ch * 4;
+            const int nbytes = ok ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(nbytes) : "memory");
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+      }
+      if (++s == S) { s = 0; u++; }
+    }
+    if (MODE == 1) asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == P) {
+    int s = 0;
+    uint32_t par = 0;
+    for (int it = blockIdx.x; it < iters_total; it += gridDim.x) {
+      mbar_wait(smem_u32(&full[s]), par);
+      if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+      __syncwarp();
+      if (++s == S) { s = 0; par ^= 1; }
+    }
+  }
+}
+
 int main() {
   const int M = 137000, C = 64;  // level-0-like table: 137k rows, 2 chunks of 32 words (256 B per row)
   std::vector<uint32_t> h((size_t)(M + 1) * C);
@@ -311,7 +387,7 @@ int main() {
       const char *pn[3] = {"random", "local2048", "local+50%zero-row"};
       for (int occ = 1; occ <= 2; occ++)
         for (int P : {1, 2, 4})
-          for (int S : {2, 4, 6, 8, 12}) {
+          for (int S : {6}) {
             size_t smem = (size_t)S * 16384 + 1024;
             if (smem * occ > 220 * 1024) continue;
             const int grid = 148 * occ;
@@ -326,6 +402,51 @@ int main() {
             printf("C: %-18s occ %d P %d S %2d: %.3f ms  %.0f GB/s  (%.1f B/clk/SM at 1.965 GHz; %.0f clk per 16 KB stage per SM)\n", pn[pattern],
                    occ, P, S, ms, gb / (ms * 1e-3), gb * 1e9 / (ms * 1e-3) / 148 / 1.965e9, ms * 1e-3 * 1.965e9 / (iters_total / 148.0));
           }
+    }
+  }
+  // ---- D ----------------------------------------------------------------------------------------------------
+  {
+    const int iters_total = 148 * 400;
+    std::vector<int> hi((size_t)iters_total * 128);
+    int *d_idx;
+    CK(cudaMalloc(&d_idx, hi.size() * 4));
+    CK(cudaFuncSetAttribute(stream2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(stream2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CUtensorMap tm2 = make_map(d_tab, M, C);  // M rows: index M is out of bounds (zero fill, no memory access)
+    for (int pattern = 0; pattern < 2; pattern++) {
+      uint64_t st = 88172645463325252ull;
+      auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+      for (int it = 0; it < iters_total; it++) {
+        const int base = (int)(rnd() % (M - 4096));
+        for (int r = 0; r < 128; r++)
+          hi[(size_t)it * 128 + r] = (pattern == 1 && rnd() % 100 < 50) ? M : base + (int)(rnd() % 2048);
+      }
+      CK(cudaMemcpy(d_idx, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+      const char *pn[2] = {"local2048", "local+50%OOB"};
+      for (int mode = 0; mode < 2; mode++)
+        for (int occ = 1; occ <= 2; occ++)
+          for (int P : {2, 4, 8, 16})
+            for (int S : {4, 6}) {
+              size_t smem = (size_t)S * 16384 + 1024;
+              if (smem * occ > 220 * 1024) continue;
+              if (32 * (P + 1) * occ > 2048) continue;
+              const int grid = 148 * occ;
+              for (int rep = 0; rep < 2; rep++) {
+                if (rep == 1) CK(cudaEventRecord(e0));
+                if (mode == 0) stream2_kernel<0><<<grid, 32 * (P + 1), smem>>>(tm2, d_tab, C, M, d_idx, iters_total, S, P, 2);
+                else stream2_kernel<1><<<grid, 32 * (P + 1), smem>>>(tm2, d_tab, C, M, d_idx, iters_total, S, P, 2);
+              }
+              CK(cudaEventRecord(e1));
+              CK(cudaDeviceSynchronize());
+              float ms;
+              CK(cudaEventElapsedTime(&ms, e0, e1));
+              double gb = (double)iters_total * 16384 / 1e9;
+              printf("D: %-14s %-22s occ %d P %2d S %d: %.3f ms  %.0f GB/s  (%.1f B/clk/SM; %.0f clk per 16 KB stage per SM)\n", pn[pattern],
+                     mode == 0 ? "gather4 uniform issue" : "cp.async 16B swizzled", occ, P, S, ms, gb / (ms * 1e-3),
+                     gb * 1e9 / (ms * 1e-3) / 148 / 1.965e9, ms * 1e-3 * 1.965e9 / (iters_total / 148.0));
+            }
     }
   }
   printf("done\n");

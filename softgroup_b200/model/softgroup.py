@@ -23,6 +23,7 @@ import torch.nn as nn
 from .. import spconv
 from ..ops import (ball_query, ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
                    voxelization_idx)
+from ..ops import instances as inst_ops
 from ..util import cuda_cast, force_fp32, rle_encode_ids
 from .blocks import MLP, ResidualBlock, UBlock
 
@@ -257,7 +258,12 @@ class SoftGroup(nn.Module):
                     ret.update(dict(pred_instances=inst,
                                     gt_instances=self.get_gt_instances(semantic_labels, instance_labels)))
                 if 'panoptic' in eval_tasks:
-                    ret.update(panoptic_preds=self.panoptic_fusion(semantic_preds.cpu().numpy(), inst))
+                    if self.sem2ins_classes or not inst or lvl_fusion:
+                        pan = self.panoptic_fusion(semantic_preds.cpu().numpy(), inst)
+                    else:  # every instance has its bitmap on the device: paste there (softgroup.py:606-639)
+                        bm, npts = self._last_instance_bitmaps
+                        pan = self.panoptic_fusion_gpu(semantic_preds, inst, bm, npts)
+                    ret.update(panoptic_preds=pan)
         if device_only:
             ret.update(semantic_preds=semantic_preds, pt_offsets=pt_offsets)
         else:
@@ -578,33 +584,22 @@ class SoftGroup(nn.Module):
         num_points = v2p_map.numel() if lvl_fusion else semantic_scores.size(0)  # length of the output masks
         nI = self.instance_classes
         cls_sm = cls_scores.softmax(1)
-        pid = proposals_idx[:, 0].long()
-        on = mask_scores[:, :nI] > mask_thr  # [sumNPoint, nI]
-        npoint = torch.zeros((num_instances, nI), dtype=torch.int32, device=on.device)
-        npoint.index_add_(0, pid, on.int())
+        mask_scores = mask_scores.contiguous()
+        # points per (proposal, class) with mask_score > thr: `mask_pred.sum(1)` of the dense procedure (:563-565)
+        npoint = inst_ops.instance_point_counts(proposals_idx.contiguous(), mask_scores, nI, mask_thr, num_instances)
         score = cls_sm[:, :nI] * iou_scores[:, :nI].clamp(0, 1)
         keep = (cls_sm[:, :nI] > cls_thr) & (npoint >= min_npoint)  # [nProp, nI]
         for i in self.sem2ins_classes:
             keep[:, i] = False
         if device_only:
-            return dict(keep=keep, score=score, npoint=npoint, on=on)
-        from ..util import rle_encode_many
-        # sort every proposal's points once (proposals_idx is in BFS order; RLE needs ascending ids)
-        pt_all = proposals_idx[:, 1].long()
-        order = torch.argsort(pid * num_points + pt_all)
-        pid_s, pt_s = pid[order], pt_all[order]
-        sel = on[order].t() & keep.t()[:, pid_s]  # [nI, sumNPoint]; row-major nonzero = class-major, proposal, pt
-        ci, pos = sel.nonzero(as_tuple=True)
-        ids = pt_s[pos].int()
-        inst_key = ci * num_instances + pid_s[pos]
-        counts = torch.bincount(inst_key, minlength=nI * num_instances)
-        kc, kp = keep.t().nonzero(as_tuple=True)  # kept (class, proposal) pairs, class-major
+            return dict(keep=keep, score=score, npoint=npoint)
+        # kept (class, proposal) pairs in the reference's order (class-major, proposal order) -> one bitmap each; run
+        # boundaries are found on the GPU and only (start, end) pairs are read back (rle.py:5-19 on the host before)
+        bitmaps, kc, kp = inst_ops.instance_bitmaps(proposals_idx.contiguous(), mask_scores, nI, mask_thr, keep, num_points)
         conf = score.t()[kc, kp]
-        cnt_kept = counts[kc * num_instances + kp]
-        ids_np = ids.cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(cnt_kept.cpu().numpy().astype(np.int64))])
+        rles = inst_ops.bitmaps_to_rle(bitmaps, num_points)
         kc_np, conf_np = kc.cpu().numpy(), conf.cpu().numpy()
-        rles = rle_encode_many(ids_np, offs, num_points)
+        self._last_instance_bitmaps = (bitmaps, num_points)  # reused by panoptic_fusion in the same forward
         instances = []
         semantic_pred = None
         k = 0
@@ -621,8 +616,26 @@ class SoftGroup(nn.Module):
                 k += 1
         return instances
 
+    def panoptic_fusion_gpu(self, semantic_preds, instance_preds, bitmaps, num_points):
+        """softgroup.py:606-639 on the GPU: `bitmaps` row k is the mask of instance_preds[k]. The visiting order is the
+        reference's own `np.argsort(scores)[::-1]` (computed here with numpy on the confidences, a few hundred floats);
+        the paste loop runs in one kernel (sgb_panoptic_paste). semantic_preds: CUDA int tensor [N]."""
+        cls_offset = self.semantic_classes - self.instance_classes - 1
+        scores = [x['conf'] for x in instance_preds]
+        order = torch.from_numpy(np.ascontiguousarray(np.argsort(scores)[::-1]).astype(np.int32)).to(semantic_preds.device)
+        cls_vals = torch.tensor([int(x['label_id']) + cls_offset for x in instance_preds], dtype=torch.int32,
+                                device=semantic_preds.device)
+        pan_cls, pan_ids = inst_ops.panoptic_paste(bitmaps, order, cls_vals, semantic_preds,
+                                                   float(self._cfg(self.test_cfg, 'panoptic_skip_iou')), num_points)
+        pan_cls, pan_ids = pan_cls.long(), pan_ids.long()
+        ignore = (pan_cls >= 11) & (pan_ids == 0)
+        preds = (pan_cls & 0xFFFF) | (pan_ids << 16)
+        preds[ignore] = self.semantic_classes
+        return preds.cpu().numpy().astype(np.uint32)
+
     def panoptic_fusion(self, semantic_preds, instance_preds):
-        """softgroup.py:606-639 (CPU numpy paste loop; SURVEY.md N3 lists it as a next row)."""
+        """softgroup.py:606-639, the reference's CPU numpy paste loop on RLE-decoded masks: kept for callers that hold host
+        results only (and as the yardstick of panoptic_fusion_gpu in the tests); the forward uses panoptic_fusion_gpu."""
         from ..util import rle_decode
         cls_offset = self.semantic_classes - self.instance_classes - 1
         panoptic_cls = semantic_preds.copy().astype(np.uint32)

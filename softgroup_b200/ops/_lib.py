@@ -6,7 +6,7 @@ an exception is raised.
 """
 import ctypes
 import os
-from ctypes import c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libsgb200.so')
@@ -56,8 +56,23 @@ SIGNATURES = {
                                       _P, c_int, c_int, c_int, _P]),
     'sgb_spconv_tc_lo_shift': (c_int, []),
     'sgb_act_split': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
+    'sgb_spconv_lo_shift': (c_int, []),
+    'sgb_spconv_overflow': (c_int, [_INTP, _P]),
+    'sgb_act_pack': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'sgb_spconv_forward_tma': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
+                                       c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    'sgb_inst_count': (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P]),
+    'sgb_bitmap_words': (c_size_t, [c_int]),
+    'sgb_inst_scatter': (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, c_int, _P]),
+    'sgb_bitmap_set': (c_int, [_P, _P, c_longlong, _P, c_int, c_int, c_int, _P]),
+    'sgb_rle_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'sgb_rle_count': (c_longlong, [_P, c_int, c_int, _P, c_size_t, _P]),
+    'sgb_rle_fill': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    'sgb_rle_format_runs': (c_longlong, [_P, _P, c_int, _P, c_longlong, _P]),
+    'sgb_bitmap_intersections': (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P]),
+    'sgb_panoptic_paste': (c_int, [_P, c_int, _P, _P, c_int, c_double, _P, _P, _P, _P]),
     'sgb_rle_format_ids': (c_longlong, [_P, _P, c_int, _P, c_longlong, _P]),
 }
 

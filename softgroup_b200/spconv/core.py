@@ -146,7 +146,7 @@ def build_down_map(indices, spatial_shape):
 CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores (default), 'ffma' = CUDA-core fp32
 
 
-def pack_weight_tc(W):
+def pack_weight_tc(W, lo_shift=None):
     """[K, Cin, Cout] f32 -> packed fp16 split for sgb_spconv_forward_tc (layout in sgb200.h):
     [K, nkc, 4 chunks, 2 (hi, lo), N, 8 halves], hi = fp16(W), lo = fp16((W - hi) * 2^sgb_spconv_tc_lo_shift());
     returned as a float32-typed buffer."""
@@ -157,23 +157,54 @@ def pack_weight_tc(W):
     Wp[:, :Cin, :Cout] = W
     Wp = Wp.view(K, nkc, 4, 8, N).permute(0, 1, 2, 4, 3).contiguous()  # [K, nkc, 4, N, 8]
     hi = Wp.half()
-    lo = ((Wp - hi.float()) * float(2 ** _lib.lib().sgb_spconv_tc_lo_shift())).half()  # same scaling as the kernels
+    if lo_shift is None:
+        lo_shift = _lib.lib().sgb_spconv_tc_lo_shift()
+    lo = ((Wp - hi.float()) * float(2 ** lo_shift)).half()  # same scaling as the kernels
     packed = torch.stack([hi, lo], dim=3).contiguous()  # [K, nkc, 4, 2, N, 8] fp16
     return packed.view(torch.float32)
 
 
 class WeightPack(object):
-    """Weight of one conv in both kernel formats: .kio [K,Cin,Cout] and the packed tcgen05 split."""
-    __slots__ = ('kio', 'packed')
+    """Weight of one conv in the kernels' formats: .kio [K,Cin,Cout] (CUDA-core kernel), .tc() the packed fp16 hi/lo
+    split of the round-1 tcgen05 kernel, .tma() the same split with the remainder scaled by 2^sgb_spconv_lo_shift() for
+    the TMA-gather kernel."""
+    __slots__ = ('kio', 'packed', 'packed2')
 
     def __init__(self, kio):
         self.kio = kio
         self.packed = None
+        self.packed2 = None
 
     def tc(self):
         if self.packed is None:
             self.packed = pack_weight_tc(self.kio)
         return self.packed
+
+    def tma(self):
+        if self.packed2 is None:
+            self.packed2 = pack_weight_tc(self.kio, lo_shift=_lib.lib().sgb_spconv_lo_shift())
+        return self.packed2
+
+
+def act_pack(feats, in_stride, in_off, C, act=None, relu=None, out=None, out_coff=0, rows=None):
+    """fp32 rows -> packed rows (per 32-channel chunk: 16 words fp16 hi pairs | 16 words lo pairs) after the optional
+    BatchNorm(eval) `act = (scale, shift)` and ReLU. `out`: an existing packed buffer [M, cpad] float32-typed (concat
+    halves); returns the packed buffer."""
+    M = feats.size(0) if rows is None else rows
+    if relu is None:
+        relu = act is not None
+    if out is None:
+        cpad = (C + 31) // 32 * 32
+        out = torch.empty((M, cpad), dtype=torch.float32, device=feats.device)
+        fill = cpad
+    else:
+        cpad = out.size(1)
+        fill = min(cpad - out_coff, (C + 31) // 32 * 32) if (out_coff + C) % 32 else C
+    scale, shift = act if act is not None else (None, None)
+    with profiler.record('act_pack', 8 * M * C):
+        check(_lib.lib().sgb_act_pack(ptr(feats), in_stride, in_off, ptr(scale), ptr(shift), int(bool(relu)), ptr(out),
+                                      cpad, out_coff, M, C, fill, _stream()), 'sgb_act_pack')
+    return out
 
 
 def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, residual=None, bias=None, out=None,
@@ -192,8 +223,17 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    use_tc = CONV_IMPL == 'tc' and Cout <= 256 and Cin <= 512
+    use_tc = CONV_IMPL in ('tc', 'tma') and Cout <= 256 and Cin <= 512
     name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
+    if use_tc and CONV_IMPL == 'tma':
+        name = 'spconv_tma_kernel' + ('' if mp is not None else '(1x1/linear)')
+        pk = act_pack(feats, in_stride, in_off, Cin, act=act, relu=act is not None)
+        with profiler.record(name, nbytes):
+            check(
+                _lib.lib().sgb_spconv_forward_tma(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.tma()), Cin, Cout,
+                                                  ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride, out_off, None, 0,
+                                                  0, None, None, 0, 0, _stream()), 'sgb_spconv_forward_tma')
+        return out
     if use_tc:
         # activation (+ split into fp16 hi/lo) once per tensor instead of once per gathered (row, offset) in the conv
         K_eff = K

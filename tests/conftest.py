@@ -62,3 +62,14 @@ def ref_model_module():
         setattr(util, n, getattr(our_util, n))
     sys.modules.setdefault('softgroup.util', util)
     return importlib.import_module('softgroup.model.softgroup')
+
+
+@pytest.fixture
+def host_instance_ops(monkeypatch):
+    """CPU tests of get_instances: the GPU bitmap ops (softgroup_b200.ops.instances) are replaced by the dense
+    reference steps of oracle/ops_cpu.py (test infrastructure), like the ball query / clustering stand-ins."""
+    from oracle import ops_cpu
+    from softgroup_b200.ops import instances as inst_ops
+    for name in ('instance_point_counts', 'instance_bitmaps', 'bitmaps_to_rle'):
+        monkeypatch.setattr(inst_ops, name, getattr(ops_cpu, name))
+    return inst_ops

@@ -89,7 +89,7 @@ def test_clusters_voxelization_reproduces_reference(monkeypatch, gold, model):
     assert np.array_equal(x.features.numpy(), gold['inst_voxel_feats'])
 
 
-def test_get_instances_reproduces_reference(gold, model):
+def test_get_instances_reproduces_reference(host_instance_ops, gold, model):
     inst = model.get_instances('x', torch.from_numpy(gold['proposals_idx']), torch.from_numpy(gold['semantic_scores']),
                                torch.from_numpy(gold['cls_scores']), torch.from_numpy(gold['iou_scores']),
                                torch.from_numpy(gold['mask_scores']))

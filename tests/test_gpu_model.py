@@ -182,6 +182,44 @@ def test_kitti_panoptic_end_to_end():
     assert sem.max() <= 19
     # things with an id carry a thing class (>= 11), stuff carries id 0 (softgroup.py:632-638)
     assert np.all(sem[ids > 0] >= 11)
+    # the forward pasted on the GPU (panoptic_fusion_gpu); the reference's numpy loop on the returned RLE masks and
+    # semantic predictions must give the same labelling (softgroup.py:606-639)
+    assert len(ret['pred_instances']) > 3
+    want = model.panoptic_fusion(ret['semantic_preds'], ret['pred_instances']) if 'semantic_preds' in ret else None
+    if want is None:  # panoptic-only result dicts carry no point-wise predictions: recompute them on the device
+        with torch.no_grad():
+            dev = harness.run_scan(model, hb, inject_pointwise=inj, device_only=True)
+        want = model.panoptic_fusion(dev['semantic_preds'].cpu().numpy(), ret['pred_instances'])
+    assert np.array_equal(pp, want)
+
+
+def test_panoptic_fusion_gpu_matches_host_loop():
+    """sgb_panoptic_paste vs the reference's paste loop (softgroup.py:606-639) on random overlapping masks, ties in
+    confidence and masks that are skipped (> 50 % covered)."""
+    from softgroup_b200.ops import instances as inst_ops
+    from softgroup_b200.util import rle_encode
+    rng = np.random.RandomState(3)
+    model = SoftGroup(**model_cfg('kitti')).eval()
+    N = 70000
+    sem = rng.randint(0, 19, N)
+    insts, rows, pts = [], [], []
+    for k in range(60):
+        c = rng.randint(0, N - 4000)
+        m = np.zeros(N, np.int64)
+        ln = rng.randint(50, 4000)
+        m[c:c + ln] = rng.rand(ln) < 0.7
+        conf = float(rng.choice([0.3, 0.5, rng.rand()]))  # ties on purpose
+        insts.append(dict(scan_id='s', label_id=int(rng.randint(1, 9)), conf=conf, pred_mask=rle_encode(m)))
+        ids = np.nonzero(m)[0]
+        rows.append(np.full(ids.size, k, np.int32))
+        pts.append(ids.astype(np.int32))
+    bm = inst_ops.bitmaps_from_pairs(torch.from_numpy(np.concatenate(rows)).cuda(), torch.from_numpy(np.concatenate(pts)).cuda(), 60, N)
+    # bitmaps -> RLE on the GPU gives back the same strings
+    assert [r['counts'] for r in inst_ops.bitmaps_to_rle(bm, N)] == [x['pred_mask']['counts'] for x in insts]
+    got = model.panoptic_fusion_gpu(torch.from_numpy(sem).cuda(), insts, bm, N)
+    want = model.panoptic_fusion(sem, insts)
+    assert np.array_equal(got, want)
+    assert len(np.unique(got >> 16)) > 10
 
 
 def test_panoptic_fusion_matches_direct_restatement():

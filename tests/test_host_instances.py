@@ -61,7 +61,7 @@ def _model(name, **test_cfg):
 
 
 @pytest.mark.parametrize('name,seed', [('scannet', 0), ('scannet', 1), ('s3dis', 2)])
-def test_get_instances_matches_dense_procedure(name, seed):
+def test_get_instances_matches_dense_procedure(host_instance_ops, name, seed):
     model = _model(name, min_npoint=8, cls_score_thr=0.02, mask_score_thr=-0.5)
     rows = 400
     pidx, sem, cls, iou, msk = _case(seed, rows, 14, model.semantic_classes, model.instance_classes)
@@ -76,7 +76,7 @@ def test_get_instances_matches_dense_procedure(name, seed):
 
 
 @pytest.mark.parametrize('name,seed', [('scannet', 3), ('s3dis', 4)])
-def test_get_instances_lvl_fusion_matches_dense_procedure(name, seed):
+def test_get_instances_lvl_fusion_matches_dense_procedure(host_instance_ops, name, seed):
     model = _model(name, min_npoint=12, cls_score_thr=0.02, mask_score_thr=-0.5)
     n_vox, n_pts = 300, 1000
     rng = np.random.RandomState(100 + seed)
