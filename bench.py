@@ -216,6 +216,131 @@ def cpu_leg(args, sd, cfg, scan, steps, warmup):
                                                     for k, v in stages.items()}), sec
 
 
+def reference_gpu_ops_leg(scan, cfg, inj, out, reps=3):
+    """The reference's OWN CUDA/CPU ops (oracle/_ref: the unmodified softgroup/ops/src compiled for sm_100a) timed on this
+    B200 on the tensors of the same scan, called the way softgroup/ops/functions.py and softgroup/model/softgroup.py call
+    them (per-class loop, relaunch when the index buffer overflows, lists copied to the host for the CPU BFS). CUDA events
+    around each call sequence; median of `reps`. Reported beside `roofline.by_kernel` -- a like-for-like kernel baseline,
+    not a target. Returns None when oracle/_ref is not on the box."""
+    import torch
+    from oracle.build_ref import load_ref
+    try:
+        ref = load_ref()
+    except Exception:
+        ref = None
+    if ref is None:
+        return None
+    from softgroup_b200 import ops as our_ops
+    g = cfg['grouping_cfg']
+    dev = torch.device('cuda')
+
+    def timed(fn):
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append((e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+        ts.sort()
+        return r, ts[len(ts) // 2]
+
+    res = {}
+    # ---- voxelize_fp (functions.py:220) ---------------------------------------------------------------------------
+    coords = torch.from_numpy(scan['coords']).to(dev)
+    vc, v2p, p2v = our_ops.voxelization_idx(coords, 1)
+    feats = torch.cat([torch.from_numpy(scan['feats']), torch.from_numpy(scan['coords_float'])], 1).to(dev).contiguous()
+    M, C = vc.size(0), feats.size(1)
+
+    def vfp():
+        o = torch.zeros((M, C), device=dev)
+        ref.voxelize_fp(feats, o, p2v, 4, M, p2v.size(1) - 1, C)
+        return o
+
+    _, (ms, wall) = timed(vfp)
+    res['voxelize_fp'] = dict(ms=ms, wall_ms=wall)
+    # ---- voxelize_idx (CPU hash, functions.py:189; the reference runs it in the dataloader and twice more in the forward)
+    ccpu = torch.from_numpy(scan['coords'])
+
+    def vidx():
+        oc, im, om = ccpu.new(), torch.IntTensor(ccpu.size(0)).zero_(), torch.IntTensor()
+        ref.voxelize_idx(ccpu, oc, im, om, 1, 4)
+
+    _, (ms, wall) = timed(vidx)
+    res['voxelize_idx_cpu'] = dict(ms=wall, wall_ms=wall)
+    # ---- grouping: per-class ballquery_batch_p (GPU, relaunch loop) + bfs_cluster (CPU, after .cpu()) -------------------
+    scores, offs = inj
+    prob = scores.softmax(-1)
+    cf = torch.from_numpy(scan['coords_float']).to(dev)
+    mean = torch.tensor(g['class_numpoint_mean'], dtype=torch.float32)
+    classes = [c for c in range(cfg['semantic_classes']) if c not in g['ignore_classes']]
+
+    def grouping():
+        t_bq = t_bfs = 0.0
+        nact = nprop = 0
+        for c in classes:
+            obj = (prob[:, c] > g['score_thr']).nonzero().view(-1)
+            if obj.size(0) < cfg['test_cfg']['min_npoint']:
+                continue
+            xyz = (cf[obj] + offs[obj]).contiguous()
+            n = xyz.size(0)
+            bi = torch.zeros(n, dtype=torch.int32, device=dev)
+            bo = torch.tensor([0, n], dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mean_active = g['mean_active']
+            while True:  # functions.py:258-266
+                idx = torch.zeros(n * mean_active, dtype=torch.int32, device=dev)
+                sl = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+                na = ref.ballquery_batch_p(xyz, bi, bo, idx, sl, n, mean_active, g['radius'])
+                if na <= n * mean_active:
+                    break
+                mean_active = int(na // n + 1)
+            idx = idx[:na]
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            ci, co = torch.IntTensor(), torch.IntTensor()
+            ref.bfs_cluster(mean, idx.cpu(), sl.cpu(), ci, co, n, float(g['npoint_thr']), int(c))  # softgroup.py:458
+            t2 = time.perf_counter()
+            t_bq += t1 - t0
+            t_bfs += t2 - t1
+            nact += int(na)
+            nprop += co.numel() - 1
+        return t_bq * 1e3, t_bfs * 1e3, nact, nprop
+
+    runs = sorted(grouping() for _ in range(reps))
+    t_bq, t_bfs, nact, nprop = runs[len(runs) // 2]
+    res['ballquery_batch_p'] = dict(ms=t_bq, nActive=nact, note='per-class calls incl. the overflow relaunches, wall clock around synchronised calls')
+    res['bfs_cluster_cpu'] = dict(ms=t_bfs, proposals=nprop, note='includes the D2H of the neighbour lists (softgroup.py:458)')
+    # ---- sec_min / sec_max / global_avg_pool on the proposals of this scan -----------------------------------------------
+    pidx, poff = out['proposals_idx'], out['proposals_offset'].contiguous()
+    if pidx.size(0) > 0:
+        pc = cf[pidx[:, 1].long()].contiguous()
+        nP = poff.numel() - 1
+
+        def secs():
+            a, b = torch.zeros((nP, 3), device=dev), torch.zeros((nP, 3), device=dev)
+            ref.sec_min(pc, poff, a, nP, 3)
+            ref.sec_max(pc, poff, b, nP, 3)
+
+        _, (ms, wall) = timed(secs)
+        res['sec_min+sec_max'] = dict(ms=ms, wall_ms=wall)
+        f32 = torch.randn((pidx.size(0), 32), device=dev)
+
+        def gap():
+            o = torch.zeros((nP, 32), device=dev)
+            ref.global_avg_pool_fp(f32, poff, o, nP, 32)
+
+        _, (ms, wall) = timed(gap)
+        res['global_avg_pool_fp'] = dict(ms=ms, wall_ms=wall, rows=int(pidx.size(0)))
+    res['note'] = ('unmodified reference ops (oracle/_ref, sm_100a build) on this B200, same scan and injected predictions; '
+                   'spconv (third party) is not part of the reference tree and has no entry here')
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -373,6 +498,13 @@ def main():
             sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
             cb, _ = cpu_leg(args, sd, cfg, scan, 1, 0)
             line['cpu_baseline'] = cb
+            try:
+                with torch.no_grad():
+                    rg = reference_gpu_ops_leg(scan, cfg, inj, out)
+                if rg is not None:
+                    line['reference_gpu_ops'] = rg
+            except Exception as e:  # a baseline leg must never take the bench line down
+                line['reference_gpu_ops'] = dict(unavailable=repr(e)[:200])
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

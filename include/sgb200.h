@@ -299,6 +299,11 @@ int sgb_bitmap_intersections(const uint32_t *d_bitmaps, int n_rows, int N, const
 int sgb_panoptic_paste(const uint32_t *d_bitmaps, int N, const int32_t *d_order, const int32_t *d_cls, int n_inst, double skip_iou,
                        uint32_t *d_prev, uint32_t *d_pan_cls, uint32_t *d_pan_ids, void *stream);
 
+/* Test-time transform of the reference dataloader, first step (softgroup/data/custom.py:87-107,162-164):
+ * out[i, :] = xyz[i, :] @ m in float64 (xyz float32 [N,3] device, m float64 [3,3] row-major HOST, out float64 [N,3] device),
+ * accumulated like the BLAS kernels numpy calls: fma(z, m2j, fma(y, m1j, x * m0j)). */
+int sgb_affine3_f64(const float *d_xyz, const double *h_m9, double *d_out, int N, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

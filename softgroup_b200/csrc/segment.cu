@@ -3,9 +3,11 @@
 // Replaces sec_mean/sec_min/sec_max (softgroup/ops/src/sec_mean/sec_mean.cu:13-93: one 32-thread block per
 // proposal, serial loop), global_avg_pool_fp/bp (roipool/roipool.cu:12-72) and get_mask_iou_* / get_mask_label
 // (cal_iou_and_masklabel/cal_iou_and_masklabel.cu:9-164: O(nInstance * len) rescans per proposal).
-// Here: segments are split into row chunks so the grid covers all SMs, reads are coalesced over the channel
-// dimension, partials are combined with warp shuffles + one atomic per (chunk, channel) for min/max (exact)
-// or a two-stage sum for mean/avg (tree order; within 1e-6 relative of the sequential sums).
+// Here: reads are coalesced over the channel dimension. min/max (order independent, exact): the ROW SPACE is cut into
+// 2048-row chunks spread over a machine-filling grid, a chunk is split at proposal boundaries, and the per-chunk partial
+// of every (proposal, channel) is combined with one atomic min/max on the sign-aware integer image of the float
+// (seg_minmax_kernel) -- 40 long proposals no longer mean 40 busy SMs. mean/avg: one CTA per proposal, shared-memory
+// tree (within 1e-6 relative of the reference's sequential sums).
 #include <float.h>
 
 #include "common.cuh"
@@ -57,6 +59,75 @@ __global__ void __launch_bounds__(kSegThreads) seg_reduce_kernel(const float *__
         out[(size_t)p * C + c] = r;
       }
       __syncthreads();
+    }
+  }
+}
+
+// ---- chunked min / max -------------------------------------------------------------------------------------------
+constexpr int kSegChunk = 2048;
+
+__device__ __forceinline__ void atomic_min_f32(float *addr, float v) {  // *addr starts at +inf; NaN never gets here
+  if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float *addr, float v) {  // *addr starts at -inf
+  if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+__global__ void seg_fill_kernel(float *__restrict__ out, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kSegThreads) seg_minmax_kernel(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
+                                                                 float *__restrict__ out, int nProposal, int C, int Cw) {
+  __shared__ float red[kSegThreads];
+  const int rows_par = kSegThreads / Cw;
+  const int tx = threadIdx.x % Cw, ty = threadIdx.x / Cw;
+  const int S = offsets[nProposal];
+  for (long long r0l = (long long)blockIdx.x * kSegChunk; r0l < S; r0l += (long long)gridDim.x * kSegChunk) {
+    int r0 = (int)r0l;
+    const int r1 = min(r0 + kSegChunk, S);
+    // proposal holding row r0: last p with offsets[p] <= r0
+    int lo = 0, hi = nProposal;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (offsets[mid] <= r0) lo = mid; else hi = mid;
+    }
+    int p = lo;
+    while (r0 < r1) {
+      while (offsets[p + 1] <= r0) p++;  // skip empty proposals
+      const int e = min(offsets[p + 1], r1);
+      for (int c0 = 0; c0 < C; c0 += Cw) {
+        const int c = c0 + tx;
+        float acc = (OP == OP_MIN) ? INFINITY : -INFINITY;
+        if (c < C)
+          for (int i = r0 + ty; i < e; i += rows_par) {
+            const float x = __ldg(&inp[(size_t)i * C + c]);
+            if (OP == OP_MIN) acc = (x < acc) ? x : acc;  // same comparison as sec_mean.cu:50 / :76 (NaN never wins)
+            else acc = (x > acc) ? x : acc;
+          }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int h = rows_par >> 1; h > 0; h >>= 1) {
+          if (ty < h) {
+            float a = red[threadIdx.x];
+            const float b = red[threadIdx.x + h * Cw];
+            if (OP == OP_MIN) a = (b < a) ? b : a; else a = (b > a) ? b : a;
+            red[threadIdx.x] = a;
+          }
+          __syncthreads();
+        }
+        if (ty == 0 && c < C) {
+          const float r = red[tx];
+          if (OP == OP_MIN) { if (r < INFINITY) atomic_min_f32(&out[(size_t)p * C + c], r); }
+          else { if (r > -INFINITY) atomic_max_f32(&out[(size_t)p * C + c], r); }
+        }
+        __syncthreads();
+      }
+      r0 = e;
     }
   }
 }
@@ -163,6 +234,15 @@ template <int OP>
 static int seg_launch(const float *inp, const int32_t *off, float *out, int nP, int C, void *stream) {
   if (nP == 0 || C == 0) return SGB_OK;
   SGB_REQUIRE(inp && off && out && nP > 0 && C > 0, SGB_ERR_ARG, "segment reduce arguments");
+  if (OP == OP_MIN || OP == OP_MAX) {
+    // an empty proposal keeps the initial value: +inf / -inf, what `1e50` / `-1e50` become as float (sec_mean.cu:47,73)
+    const long long n = (long long)nP * C;
+    seg_fill_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, OP == OP_MIN ? INFINITY : -INFINITY);
+    SGB_LAUNCH_CHECK();
+    seg_minmax_kernel<OP><<<kNumSMs * 4, kSegThreads, 0, (cudaStream_t)stream>>>(inp, off, out, nP, C, pow2_cw(C));
+    SGB_LAUNCH_CHECK();
+    return SGB_OK;
+  }
   seg_reduce_kernel<OP><<<std::min(nP, 65535), kSegThreads, 0, (cudaStream_t)stream>>>(inp, off, out, nP, C, pow2_cw(C));
   SGB_LAUNCH_CHECK();
   return SGB_OK;

@@ -107,3 +107,77 @@ def calibrate_heads(model, host_batch, logit=6.0, ridge=1e-3):
     acc = (scores.argmax(1) == sem).float().mean().item()
     res = (offs - off_t)[inst]
     return dict(sem_acc=acc, offset_residual_sigma=res.std().item(), offset_label_sigma=off_t[inst].std().item())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Test-time data preparation on the GPU: CustomDataset.transform_test + collate_fn
+# (softgroup/data/custom.py:162-168, 191-256) and the S3DIS x4 split (softgroup/data/s3dis.py:46-115) from RAW points.
+# ---------------------------------------------------------------------------------------------------------------------
+def _test_rotation():
+    """dataAugment with every augmentation off (custom.py:87-107): m = eye(3) @ rot_z(0.35 pi), float64 like numpy."""
+    import math
+    m = np.eye(3)
+    theta = 0.35 * math.pi
+    return np.matmul(m, [[math.cos(theta), math.sin(theta), 0], [-math.sin(theta), math.cos(theta), 0], [0, 0, 1]])
+
+
+def transform_test_gpu(xyz, scale, x4_split=False):
+    """xyz float32 [N,3] CUDA (already centred like prepare_data_inst.py:55) -> (coords int64 [N,4] with the batch column,
+    coords_float float32 [N,3], order int64 [N] or None). Same arithmetic as the reference: float64 rotation, `* scale`,
+    `- min`, `.long()` truncation; with x4_split the four interleaved pieces (inds[k::4]) are shifted by their OWN minimum
+    and concatenated piece-major (s3dis.py:53-75) -- `order` is that permutation of the input points."""
+    import ctypes
+    from .ops import _lib
+    from .ops._lib import check, ptr
+    assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()
+    N = xyz.size(0)
+    m = np.ascontiguousarray(_test_rotation(), dtype=np.float64)
+    mid = torch.empty((N, 3), dtype=torch.float64, device=xyz.device)
+    check(_lib.lib().sgb_affine3_f64(ptr(xyz), m.ctypes.data_as(ctypes.c_void_p), ptr(mid), N,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'sgb_affine3_f64')
+    if not x4_split:
+        s = mid * float(scale)
+        s = s - s.min(0)[0]
+        coords = torch.cat([torch.zeros((N, 1), dtype=torch.int64, device=xyz.device), s.long()], 1)
+        return coords, mid.float(), None
+    order = torch.cat([torch.arange(k, N, 4, device=xyz.device) for k in range(4)])
+    pieces, pos = [], 0
+    for k in range(4):
+        n_k = (N - k + 3) // 4
+        s = mid[order[pos:pos + n_k]] * float(scale)
+        s = s - s.min(0)[0]
+        pieces.append(torch.cat([torch.full((n_k, 1), k, dtype=torch.int64, device=xyz.device), s.long()], 1))
+        pos += n_k
+    return torch.cat(pieces, 0), mid[order].float(), order
+
+
+def prepare_test_batch_gpu(xyz, rgb, semantic_label=None, instance_label=None, scale=50, min_spatial_shape=128,
+                           x4_split=False, scan_id='scan'):
+    """Raw per-point arrays (numpy or tensors; xyz float32 [N,3], rgb float32 [N,C]) -> the reference collate dict
+    (custom.py:240-256 / s3dis.py:99-115) with every tensor on the GPU and the point->voxel hash done there. Labels are
+    passed through (their instance re-labelling and offset labels are evaluation inputs, not part of the forward)."""
+    dev = torch.device('cuda')
+    as_t = (lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(dev, non_blocking=True).to(dt))
+    xyz_t = as_t(xyz, torch.float32).contiguous()
+    coords, coords_float, order = transform_test_gpu(xyz_t, scale, x4_split=x4_split)
+    feats = as_t(rgb, torch.float32)
+    sem = as_t(semantic_label, torch.int64) if semantic_label is not None else None
+    ins = as_t(instance_label, torch.int64) if instance_label is not None else None
+    if order is not None:
+        feats = feats[order]
+        sem = sem[order] if sem is not None else None
+        ins = ins[order] if ins is not None else None
+    n_batch = 4 if x4_split else 1
+    spatial_shape = np.clip(coords.max(0)[0][1:].cpu().numpy() + 1, min_spatial_shape, None)
+    voxel_coords, v2p_map, p2v_map = ops.voxelization_idx(coords.contiguous(), n_batch)
+    return dict(scan_ids=[scan_id], coords=coords, batch_idxs=(torch.zeros_like(coords[:, 0].int()) if x4_split else coords[:, 0].int()),
+                voxel_coords=voxel_coords, p2v_map=p2v_map, v2p_map=v2p_map, coords_float=coords_float, feats=feats.contiguous(),
+                semantic_labels=sem, instance_labels=ins, spatial_shape=spatial_shape, batch_size=n_batch)
+
+
+def run_scan_raw(model, xyz, rgb, semantic_label=None, instance_label=None, scale=50, min_spatial_shape=128, x4_split=False,
+                 scan_id='scan', **kw):
+    """End to end from RAW points: GPU test transform + GPU hashing + forward (the call N2 adds in front of run_scan)."""
+    b = prepare_test_batch_gpu(xyz, rgb, semantic_label, instance_label, scale, min_spatial_shape, x4_split, scan_id)
+    b.pop('coords')
+    return model.forward_test(**b, **kw)

@@ -73,6 +73,7 @@ SIGNATURES = {
     'sgb_rle_format_runs': (c_longlong, [_P, _P, c_int, _P, c_longlong, _P]),
     'sgb_bitmap_intersections': (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P]),
     'sgb_panoptic_paste': (c_int, [_P, c_int, _P, _P, c_int, c_double, _P, _P, _P, _P]),
+    'sgb_affine3_f64': (c_int, [_P, _P, _P, c_int, _P]),
     'sgb_rle_format_ids': (c_longlong, [_P, _P, c_int, _P, c_longlong, _P]),
 }
 
