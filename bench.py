@@ -27,6 +27,24 @@ if ROOT not in sys.path:
 METRIC = 'scans/sec on 150k-pt ScanNet-shape synth'
 WORKLOAD = 'c2_scannet'
 N_POINTS = 150000
+# BASELINE.json configs (index -> key). `c2` is the configuration the metric is quoted on and the default; the others are
+# the same hot path at the other configs' full sizes (bench lines for context, selected with --workload).
+WORKLOADS = {
+    'c2': dict(cfg='scannet', shape='c2_scannet', n=150000, sigma=0.03, metric=METRIC,
+               what='ScanNet-shape synthetic scan (~150k pts, 18 classes), full SoftGroup inference, one scan per GPU per step'),
+    'c2frag': dict(cfg='scannet', shape='c2_scannet', n=150000, sigma=0.03, fragments=6, confusion=0.15,
+                   metric=METRIC + ' (fragmented predictions: hundreds of proposals)',
+                   what='ScanNet-shape scan as c2, point-wise predictions of a noisy checkpoint: objects split into up to 6 '
+                        'fragments, 15 % of the instance points carry a second class'),
+    'c3': dict(cfg='s3dis', shape='c3_s3dis', n=800000, sigma=0.03, x4=True, metric='rooms/sec on 800k-pt S3DIS-shape synth',
+               what='S3DIS-Area5-shape synthetic room (~800k pts, 13 classes), x4_split backbone, grouping on all points'),
+    'c4': dict(cfg='kitti', shape='c4_kitti', n=120000, sigma=0.05, intensity_only=True,
+               metric='sweeps/sec on 120k-pt SemanticKITTI-shape synth',
+               what='SemanticKITTI-shape synthetic sweep (~120k pts), panoptic config, one sweep per GPU per step'),
+    'c5': dict(cfg='stpls3d++', shape='c5_stpls3d', n=1500000, sigma=0.3, no_coords=True,
+               metric='tiles/sec on 1.5M-pt STPLS3D-shape synth',
+               what='STPLS3D-shape synthetic tile (~1.5M pts), SoftGroup++ pyramid + octree path, one tile per GPU per step'),
+}
 
 
 def parse():
@@ -38,6 +56,7 @@ def parse():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-points', type=int, default=20000)
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     return ap.parse_args()
 
 
@@ -352,9 +371,22 @@ def main():
     from softgroup_b200 import synth
     from softgroup_b200.configs import model_cfg
 
-    cfg = model_cfg('scannet')
+    wl = WORKLOADS[args.workload]
+    cfg = model_cfg(wl['cfg'])
+
+    def make_workload_scan(seed):
+        sc = synth.make_scan(wl['shape'], seed=seed, n_points=wl['n'])
+        if wl.get('intensity_only'):
+            sc['feats'] = sc['feats'][:, :1].copy()
+        if wl.get('no_coords'):
+            pass  # with_coords=False in the model config: feats stay rgb
+        if wl.get('x4'):
+            sc = synth.to_x4_split(sc)
+        return sc
 
     if args.impl == 'reference':
+        assert args.workload == 'c2', 'the reference arm is defined on the metric configuration (c2)'
+
         if rank != 0:
             return 0
         from softgroup_b200.model import SoftGroup
@@ -389,9 +421,10 @@ def main():
 
     torch.manual_seed(0)
     model = SoftGroup(**cfg).cuda().eval()
-    scan = synth.make_scan(WORKLOAD, seed=args.seed + rank, n_points=N_POINTS)
+    scan = make_workload_scan(args.seed + rank)
     hb = harness.to_host_batch(scan, pin=True)
-    inj = harness.pointwise_injection(scan, sigma=0.03, seed=args.seed + rank)
+    inj = harness.pointwise_injection(scan, sigma=wl['sigma'], seed=args.seed + rank, fragments=wl.get('fragments', 1),
+                                      confusion=wl.get('confusion', 0.0))
     dev = harness.device_batch(hb)
     dev_in = {k: v for k, v in dev.items() if k not in ('voxel_coords', 'v2p_map', 'p2v_map')}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda')
@@ -446,7 +479,12 @@ def main():
     launches_per_step = launches // (args.steps + max(args.warmup, 3))
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device='cuda')
+    per_rank = None
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)  # a few bytes over NCCL: per-rank timings, so that a slow rank is visible in the line
+        per_rank = dict(device_ms_per_step=[round(float(x[0]) / args.steps, 3) for x in allt],
+                        e2e_ms_per_step=[round(float(x[1]) / args.steps, 3) for x in allt])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
     value = world * args.steps / (dev_ms_max / 1e3)
@@ -478,14 +516,14 @@ def main():
         if isinstance(ret, dict):
             d2h = int(sum(v.nbytes for v in ret.values() if isinstance(v, np.ndarray)))
             d2h += int(sum(len(p['pred_mask']['counts']) for p in ret.get('pred_instances', [])))
-        line = dict(metric=METRIC, value=value, unit='scans/sec', n_gpus=world, steps=args.steps,
+        line = dict(metric=wl['metric'], value=value, unit='scans/sec', n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=dev_ms_max / args.steps, higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                    config=dict(workload='ScanNet-shape synthetic scan (~150k pts, 18 classes), full SoftGroup '
-                                'inference, one scan per GPU per step', points=N_POINTS,
-                                path='softgroup_scannet.yaml hyper-parameters (32 channels x 7 U-Net levels), random-init '
-                                'weights; point-wise head outputs are computed, then overwritten by synthetic predictions '
-                                '(one-hot*8+N(0,1), centroid offsets+N(0,3cm)) so grouping sees a trained-checkpoint load',
+                    config=dict(workload=wl['what'], workload_key=args.workload, points=wl['n'],
+                                path='%s hyper-parameters (%d channels x %d U-Net levels), random-init weights; point-wise head '
+                                'outputs are computed, then overwritten by synthetic predictions (one-hot*8+N(0,1), centroid '
+                                'offsets+N(0,sigma)) so grouping sees a trained-checkpoint load' %
+                                (wl['cfg'], cfg['channels'], cfg['num_blocks']),
                                 l2='flushed: 512 MiB memset between timed steps',
                                 parallelism='dp%d (independent scans, no data-path collective)' % world,
                                 proposals=int(out['proposals_offset'].numel() - 1),
@@ -494,7 +532,9 @@ def main():
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms_max / args.steps),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     clocks=sampler.summary(), roofline=roofline, stage_ms=prof.get('stage_ms'))
-        if not args.no_cpu_baseline and world == 1:
+        if per_rank is not None:
+            line['per_rank'] = per_rank
+        if not args.no_cpu_baseline and world == 1 and args.workload == 'c2':
             sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
             cb, _ = cpu_leg(args, sd, cfg, scan, 1, 0)
             line['cpu_baseline'] = cb

@@ -13,11 +13,27 @@ from softgroup_b200.spconv import core  # noqa: E402
 from softgroup_b200.ops import _lib  # noqa: E402
 from softgroup_b200.ops._lib import check, ptr  # noqa: E402
 
-impls = sys.argv[1:] or ['tc', 'tma']
+impls = [a for a in sys.argv[1:] if not a.startswith('--')] or ['tc', 'tma']
+ORDER = 'morton' if '--morton' in sys.argv else 'orig'
+
+
+def part1by2(v):
+    v = v & 0x1fffff
+    v = (v | (v << 32)) & 0x1f00000000ffff
+    v = (v | (v << 16)) & 0x1f0000ff0000ff
+    v = (v | (v << 8)) & 0x100f00f00f00f00f
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3
+    v = (v | (v << 2)) & 0x1249249249249249
+    return v
 scan = synth.make_scan('c2_scannet', seed=0)
 coords = torch.from_numpy(scan['coords']).cuda()
 vc, v2p, p2v = ops.voxelization_idx(coords, 1)
 idx = vc.int().contiguous()
+if ORDER == 'morton':  # rows in Z-order: a 128-row tile is a compact blob, its 27-neighbourhoods overlap
+    c = idx.long()
+    key = (c[:, 0] << 60) | part1by2(c[:, 1]) | (part1by2(c[:, 2]) << 1) | (part1by2(c[:, 3]) << 2)
+    idx = idx[torch.argsort(key)].contiguous()
+print('row order:', ORDER, flush=True)
 shape = [int(s) for s in scan['spatial_shape']]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda')
 L = _lib.lib()

@@ -561,14 +561,14 @@ int sgb_spconv_forward_tma(const float *d_in_pk, int in_stride, int Min, const i
   p.items = tiles * p.nparts;
   const size_t b_stage = (size_t)NT * 128;
   const size_t map_bytes = 2 * (size_t)K * T2_ROWS * 4;
-  const size_t budget = 220 * 1024;
+  const size_t budget = 216 * 1024;  // + ~1.2 KB of static shared memory (barriers, lists) must stay within 227 KB per CTA
   int S = (int)((budget - map_bytes - 1024) / (T2_A_BYTES + b_stage));
   S = std::max(2, std::min(S, T2_MAXS));
   p.S = S;
   const size_t smem = (size_t)S * (T2_A_BYTES + b_stage) + map_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   const int grid = std::min(p.items, sms);

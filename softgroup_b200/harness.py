@@ -38,10 +38,10 @@ def h2d_bytes(batch):
     return int(sum(v.numel() * v.element_size() for v in batch.values() if isinstance(v, torch.Tensor)))
 
 
-def pointwise_injection(scan, sigma=0.03, seed=0, logit=8.0):
+def pointwise_injection(scan, sigma=0.03, seed=0, logit=8.0, fragments=1, confusion=0.0):
     """Device-resident synthetic point-wise predictions (see SoftGroup.forward_test `inject_pointwise`)."""
     from . import synth
-    scores, off = synth.grouping_inputs(scan, sigma=sigma, seed=seed, logit=logit)
+    scores, off = synth.grouping_inputs(scan, sigma=sigma, seed=seed, logit=logit, fragments=fragments, confusion=confusion)
     return torch.from_numpy(scores).cuda(), torch.from_numpy(off).cuda()
 
 
@@ -52,7 +52,7 @@ def run_scan(model, host_batch, device_only=False, inject_pointwise=None):
     voxel_coords, v2p_map, p2v_map = ops.voxelization_idx(dev['coords'], dev['batch_size'])
     dev.update(voxel_coords=voxel_coords, v2p_map=v2p_map, p2v_map=p2v_map)
     dev.pop('coords')
-    return model.forward_test(device_only=device_only, inject_pointwise=inject_pointwise, **dev)
+    return model.forward_test(device_only=device_only, inject_pointwise=inject_pointwise, host_inputs=host_batch, **dev)
 
 
 def device_batch(host_batch):

@@ -186,6 +186,11 @@ class SoftGroup(nn.Module):
         self._events = []
         self._mark('start')
         device_only = kwargs.get('device_only', False)  # bench: keep results on the GPU (no numpy / RLE)
+        # The reference returns the caller's own inputs (labels, coords_float, feats) as numpy arrays, reading them back from
+        # the GPU (softgroup.py:317-331). When the caller still holds them on the host (harness.run_scan), `host_inputs`
+        # hands those tensors over and the result dict carries views of them: 7.8 of the 12.3 MB read back per 150k-point
+        # scan were these copies.
+        host_inputs = kwargs.get('host_inputs', None)
         tc = self.test_cfg
         eval_tasks = self._cfg(tc, 'eval_tasks', ['semantic', 'instance'])
         x4_split = self._cfg(tc, 'x4_split', False)
@@ -223,17 +228,25 @@ class SoftGroup(nn.Module):
         # the reference reads these back with blocking .cpu() calls in the middle of the forward (softgroup.py:317-331);
         # here the copies go to pinned memory on a side stream and are awaited once, after the instance branch
         fetch = _HostFetcher(semantic_scores.device) if not device_only else None
+
+        def passthrough(name, dev_tensor, host_key):
+            h = host_inputs.get(host_key) if (host_inputs is not None and not x4_split) else None
+            if h is not None and torch.is_tensor(h) and not h.is_cuda and dev_tensor is not None and h.shape == dev_tensor.shape:
+                fetch.add(name, h)  # CPU tensors pass through the fetcher untouched (numpy view of the caller's buffer)
+            else:
+                fetch.add(name, dev_tensor)
+
         if not device_only:
             if 'semantic' in eval_tasks or 'panoptic' in eval_tasks:
-                fetch.add('semantic_labels', semantic_labels)
-                fetch.add('instance_labels', instance_labels)
+                passthrough('semantic_labels', semantic_labels, 'semantic_labels')
+                passthrough('instance_labels', instance_labels, 'instance_labels')
             if 'semantic' in eval_tasks:
-                fetch.add('coords_float', coords_float)
-                fetch.add('color_feats', color_feats)
+                passthrough('coords_float', coords_float, 'coords_float')
+                passthrough('color_feats', color_feats, 'feats')
                 # get_point_wise_results (softgroup.py:524-536): voxel predictions go back to points under lvl_fusion
                 fetch.add('semantic_preds', semantic_preds[v2p_map.long()] if lvl_fusion else semantic_preds)
                 fetch.add('offset_preds', pt_offsets[v2p_map.long()] if lvl_fusion else pt_offsets)
-                fetch.add('offset_labels', pt_offset_labels)
+                passthrough('offset_labels', pt_offset_labels, 'pt_offset_labels')
         if not self.semantic_only and ('instance' in eval_tasks or 'panoptic' in eval_tasks):
             if lvl_fusion:  # softgroup.py:332-334
                 batch_idxs = input.indices[:, 0].int().contiguous()
@@ -255,8 +268,9 @@ class SoftGroup(nn.Module):
                 ret.update(device_instances=inst, proposals_idx=proposals_idx, proposals_offset=proposals_offset)
             else:
                 if 'instance' in eval_tasks:
-                    ret.update(dict(pred_instances=inst,
-                                    gt_instances=self.get_gt_instances(semantic_labels, instance_labels)))
+                    ret.update(dict(pred_instances=inst))
+                    # softgroup.py:353: computed on the device, read back with the other arrays (no blocking .cpu() here)
+                    fetch.add('gt_instances', self._gt_instances_tensor(semantic_labels, instance_labels))
                 if 'panoptic' in eval_tasks:
                     if self.sem2ins_classes or not inst or lvl_fusion:
                         pan = self.panoptic_fusion(semantic_preds.cpu().numpy(), inst)
@@ -661,8 +675,7 @@ class SoftGroup(nn.Module):
         panoptic_preds[ignore_inds] = self.semantic_classes
         return panoptic_preds.astype(np.uint32)
 
-    def get_gt_instances(self, semantic_labels, instance_labels):
-        """softgroup.py:641-653."""
+    def _gt_instances_tensor(self, semantic_labels, instance_labels):
         label_shift = self.semantic_classes - self.instance_classes
         semantic_labels = semantic_labels - label_shift + 1
         semantic_labels[semantic_labels < 0] = 0
@@ -670,4 +683,8 @@ class SoftGroup(nn.Module):
         ignore_inds = instance_labels < 0
         gt_ins = semantic_labels * 1000 + instance_labels
         gt_ins[ignore_inds] = 0
-        return gt_ins.cpu().numpy()
+        return gt_ins
+
+    def get_gt_instances(self, semantic_labels, instance_labels):
+        """softgroup.py:641-653."""
+        return self._gt_instances_tensor(semantic_labels, instance_labels).cpu().numpy()

@@ -151,15 +151,43 @@ def make_scan(shape='c2_scannet', seed=0, n_points=None, batch_id=0):
     )
 
 
-def grouping_inputs(scan, sigma=0.03, seed=0, logit=8.0):
+def grouping_inputs(scan, sigma=0.03, seed=0, logit=8.0, fragments=1, confusion=0.0):
     """Stage inputs for forward_grouping (SURVEY.md 8(d) fallback): semantic scores = one-hot*logit + N(0,1),
-    pt_offsets = (centroid - xyz) + N(0, sigma)."""
+    pt_offsets = (centroid - xyz) + N(0, sigma).
+
+    fragments > 1 / confusion > 0 give the load of a REAL checkpoint on a real scan (hundreds of proposals with
+    fragments, not one clean proposal per object): every object is cut into up to `fragments` spatial parts (k-means-like
+    split along its longest axes) whose points shift to the PART's centroid, and a share `confusion` of the instance points
+    carries a second plausible class (logit - 1 instead of noise), so the same points are clustered under two classes."""
     rng = np.random.RandomState(seed + 1000)
     n = scan['coords_float'].shape[0]
     scores = rng.randn(n, scan['n_semantic']).astype(np.float32)
     scores[np.arange(n), scan['semantic_labels']] += logit
-    off = scan['pt_offset_labels'] + (rng.randn(n, 3) * sigma).astype(np.float32)
-    off[scan['instance_labels'] < 0] = 0
+    target = scan['pt_offset_labels'].astype(np.float32).copy()
+    inst = scan['instance_labels']
+    if fragments > 1:
+        xyz = scan['coords_float']
+        order = np.argsort(inst, kind='stable')
+        bounds = np.flatnonzero(np.diff(inst[order])) + 1
+        for seg in np.split(order, bounds):
+            if inst[seg[0]] < 0 or seg.size < 200:
+                continue
+            k = int(rng.randint(2, fragments + 1))
+            p = xyz[seg]
+            axis = int(np.argmax(p.max(0) - p.min(0)))
+            cuts = np.quantile(p[:, axis], np.sort(rng.uniform(0.1, 0.9, k - 1)))
+            part = np.searchsorted(cuts, p[:, axis])
+            for q in range(k):
+                sel = seg[part == q]
+                if sel.size:
+                    target[sel] = xyz[sel].mean(0) - xyz[sel]
+    if confusion > 0:
+        cand = np.flatnonzero(inst >= 0)
+        pick = cand[rng.rand(cand.size) < confusion]
+        alt = rng.randint(2, scan['n_semantic'], pick.size)
+        scores[pick, alt] += logit - 1.0
+    off = target + (rng.randn(n, 3) * sigma).astype(np.float32)
+    off[inst < 0] = 0
     return scores, off.astype(np.float32)
 
 

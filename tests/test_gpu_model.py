@@ -169,7 +169,9 @@ def test_kitti_panoptic_end_to_end():
     scan = synth.make_scan('c4_kitti', seed=0, n_points=40000)
     scan['feats'] = scan['feats'][:, :1].copy()  # intensity only
     torch.manual_seed(0)
-    model = SoftGroup(**model_cfg('kitti')).cuda().eval()
+    # the yaml evaluates 'panoptic' only; 'instance' is added here so that the result dict also carries the instances the
+    # fusion was computed from (the forward itself is the same)
+    model = SoftGroup(**model_cfg('kitti', test_cfg=dict(eval_tasks=['panoptic', 'instance']))).cuda().eval()
     hb = harness.to_host_batch(scan)
     inj = harness.pointwise_injection(scan, sigma=0.05, seed=0)
     with torch.no_grad():
