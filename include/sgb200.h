@@ -228,11 +228,12 @@ int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scal
                   float *d_y, int M, int C, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Round-2 sparse convolution (spconv_tma.cu): same contraction as sgb_spconv_forward_tc, input rows fetched by TMA row
- * gather (cp.async.bulk.tensor ... tile::gather4) from PACKED activations, persistent CTAs, fused output packing.
+ * Round-2 sparse convolution (spconv_ss.cu): same contraction as sgb_spconv_forward_tc; input rows of PACKED activations
+ * gathered by a deep cp.async ring straight into the swizzled shared-memory operand of tcgen05.mma, persistent CTAs,
+ * accumulators double-buffered in tensor memory, fused output packing.
  * Packed rows: per 32-channel chunk 16 words of fp16 hi pairs then 16 words of fp16 lo pairs, x = hi + lo * 2^-shift with
  * shift = sgb_spconv_lo_shift() (weights packed by the host with the same shift: [K][nkc][4][2][N][8 halves]).
- *   d_in_pk [Min rows][in_stride words]; row index Min stands for "no neighbour" (out of bounds: read as zero).
+ *   d_in_pk [Min rows][in_stride words]; rulebook entry -1 = no neighbour (zero row).
  *   outputs (either or both): d_out fp32 rows (strided like sgb_spconv_forward_tc); d_pk_out packed rows written at
  *   channel offset pk_coff (multiple of 8) after y = relu?(x * pk_scale[c] + pk_shift[c]) per OUTPUT channel c -- the
  *   consumer's BatchNorm(eval)+ReLU folded into this producer; pk_fill != 0 also zeroes the upper half of a last chunk
@@ -245,7 +246,7 @@ int sgb_spconv_lo_shift(void);
 int sgb_spconv_overflow(int *h_flag, void *stream);
 int sgb_act_pack(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
                  float *d_pk, int pk_stride, int pk_coff, int M, int C, int Cfill, void *stream);
-int sgb_spconv_forward_tma(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
+int sgb_spconv_forward_ss(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
                            const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
                            const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
                            int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill,
@@ -303,6 +304,7 @@ int sgb_panoptic_paste(const uint32_t *d_bitmaps, int N, const int32_t *d_order,
  * out[i, :] = xyz[i, :] @ m in float64 (xyz float32 [N,3] device, m float64 [3,3] row-major HOST, out float64 [N,3] device),
  * accumulated like the BLAS kernels numpy calls: fma(z, m2j, fma(y, m1j, x * m0j)). */
 int sgb_affine3_f64(const float *d_xyz, const double *h_m9, double *d_out, int N, void *stream);
+
 
 #ifdef __cplusplus
 }

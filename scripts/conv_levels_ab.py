@@ -1,5 +1,5 @@
 """Per-level timing of one SubM 3x3x3 convolution (C_l -> C_l) on the rulebooks of the 150k-point bench scan, for the
-conv implementations named on the command line (default: tc tma). L2 is flushed before every timed launch; the packed
+conv implementations named on the command line (default: tc ss). L2 is flushed before every timed launch; the packed
 input is prepared outside the timed region so the number is the conv kernel alone.
 Usage: python scripts/conv_levels_ab.py [impl ...]"""
 import sys
@@ -13,7 +13,7 @@ from softgroup_b200.spconv import core  # noqa: E402
 from softgroup_b200.ops import _lib  # noqa: E402
 from softgroup_b200.ops._lib import check, ptr  # noqa: E402
 
-impls = [a for a in sys.argv[1:] if not a.startswith('--')] or ['tc', 'tma']
+impls = [a for a in sys.argv[1:] if not a.startswith('--')] or ['tc', 'ss']
 ORDER = 'morton' if '--morton' in sys.argv else 'orig'
 
 
@@ -65,7 +65,7 @@ for lvl, C, M, mp in levels:
             pk = core.act_pack(x, C, 0, C)
 
             def run():
-                check(L.sgb_spconv_forward_tma(ptr(pk), C, M, ptr(mp), 27, M, ptr(W.tma()), C, C, None, 0, 0, None, ptr(out), C, 0,
+                check(L.sgb_spconv_forward_ss(ptr(pk), C, M, ptr(mp), 27, M, ptr(W.ss()), C, C, None, 0, 0, None, ptr(out), C, 0,
                                                None, 0, 0, None, None, 0, 0, core._stream()))
         for _ in range(2):
             run()

@@ -61,6 +61,21 @@ __global__ void bfs_init_kernel(int N, BfsWs w) {
   w.size[v] = 0;
 }
 
+// L1-cached read of a word that other CTAs lower with atomics during the same kernel (ld.global.ca): the value may be
+// STALE, i.e. higher than the current one (labels and claim keys only ever decrease) -- the caller then merely issues an
+// atomicMin that the memory system resolves. Neighbour lists stay inside one object (a few thousand nodes, tens of KB),
+// so these reads hit L1 instead of paying an L2 round trip per edge.
+__device__ __forceinline__ int32_t ld_ca_i32(const int32_t *p) {
+  int32_t v;
+  asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_ca_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
 // Label propagation, one warp per source node: the (pointer-chased) label of u is pushed to every listed v. A node
 // re-reads its list only when its chased label is lower than the one it pushed last time (`w.wins`, idle until the
 // emit phase, keeps the last pushed label): every pass chases every node's label (2-3 words per node) but the 4 bytes
@@ -93,7 +108,7 @@ __global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, 
     int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
     for (int j = lane; j < l; j += 32) {
       int v = __ldg(&idxs[(size_t)s + j]);
-      if (label[v] > lu) atomicMin(&w.label[v], lu);
+      if (ld_ca_i32(&w.label[v]) > lu) atomicMin(&w.label[v], lu);  // a stale (higher) value only costs a redundant atomic
     }
     __syncwarp();
     if (lane == 0) w.wins[u] = lu;
@@ -334,7 +349,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
             v[t] = (j < l) ? __ldg(&idxs[(size_t)s + j]) : -1;
           }
 #pragma unroll
-          for (int t = 0; t < 4; t++) k[t] = (v[t] >= 0) ? __ldcg(&w.key[v[t]]) : 0ull;
+          for (int t = 0; t < 4; t++) k[t] = (v[t] >= 0) ? ld_ca_u64(&w.key[v[t]]) : 0ull;  // stale = higher: see ld_ca_*
 #pragma unroll
           for (int t = 0; t < 4; t++) {
             if (v[t] < 0) continue;

@@ -1,29 +1,31 @@
-// spconv_tma.cu -- sparse convolution, round-2 kernel: persistent CTAs, TMA row gather, tcgen05 with both operands
-// in shared memory, accumulators double-buffered in tensor memory, fused activation/split epilogue (sm_100a).
+// spconv_ss.cu -- sparse convolution, round-2 kernel: persistent CTAs, a deep cp.async gather ring, tcgen05 with both
+// operands in shared memory, accumulators double-buffered in tensor memory, fused activation/split epilogue (sm_100a).
 //
 // Data: every activation tensor lives in HBM as PACKED rows -- per 32-channel chunk one 128-byte line
 // [16 words of fp16 hi pairs | 16 words of fp16 lo pairs], x = hi + lo * 2^-kLoShift (error-compensated fp16 pair,
 // fp32-grade products hi*hi + hi*lo + lo*hi accumulated in fp32). The convolution is output stationary:
 // a work item is a tile of 128 output rows x NT output columns; for every kernel offset with an active pair in the
 // tile and every 32-channel chunk of Cin ("iteration"):
-//   * the 128 input row slices (128 B each) are fetched by the TMA unit itself: cp.async.bulk.tensor.2d ...
-//     tile::gather4 takes four row indices of the rulebook per instruction and lands the rows in a SWIZZLE_128B
-//     K-major tile in shared memory (the layout tcgen05.mma reads) -- no registers, no L1 tag look-ups, the bytes in
-//     flight are bounded by the ring depth, not by the register file (round 1 was gather-latency bound: every lane of
-//     8 producer warps read a different 128-byte line into registers). An absent neighbour is row index Min: the
-//     tensor map has Min rows, so the TMA unit zero-fills it;
+//   * the 128 input row slices (128 B each, row indices from the rulebook slice in shared memory) are copied by
+//     cp.async, 16 bytes per lane -- the 8 lanes of a quarter-warp fetch ONE whole line, a warp instruction 4 lines --
+//     straight into the SWIZZLE_128B K-major tile tcgen05.mma reads (chunk position ^ (row & 7)); an absent neighbour
+//     is a zero-fill copy (source size 0). Completion is tracked per stage by cp.async.mbarrier.arrive.noinc, so the
+//     copies of S = 6..10 iterations are in flight per CTA without holding a register. Why: the round-1 kernel kept the
+//     gathered rows in REGISTERS (two slices per producer thread), i.e. a prefetch distance of one iteration -- its
+//     iteration time equalled the L2/DRAM latency (1457 cycles per pair measured) at a few per cent of the L1/L2 bandwidth.
+//     TMA row gather (cp.async.bulk.tensor tile::gather4) was built and measured first: 20 cycles per 512-byte
+//     instruction and SM (<= 31 B/clk/SM, scripts/tma_probe.cu; 2-3x slower per level, profiles/r2_*), so it is not used;
 //   * the weight slice [B_hi | B_lo] (pre-split, pre-packed in core-matrix order by the host) arrives by
-//     cp.async.bulk on the same stage barrier;
+//     cp.async.bulk (TMA bulk copy) on the same stage barrier;
 //   * one elected lane issues  D[:, 0:2nt] += A_hi [B_hi | B_lo],  D[:, nt:2nt] += A_lo B_hi  per 16-channel k-step
 //     (tcgen05.mma.cta_group::1.kind::f16, M = 128, A and B from shared-memory descriptors) and commits the stage back.
 // The CTA is persistent (grid = #SMs) and walks work items round-robin. Accumulators are double-buffered in TMEM: the
 // epilogue warps drain tile j (tcgen05.ld -> + bias + residual -> optional fp32 rows, optional NEXT layer's
 // BatchNorm+ReLU -> fp16 hi/lo split -> packed rows) while the pipeline already runs tile j+1; the rulebook slice of
 // tile j+1 is prefetched into registers during tile j's gathers.
-// Warp roles (320 threads): 0-3 rulebook + gather issue, 4 MMA issue, 5 weight loader, 6-9 epilogue.
+// Warp roles (448 threads): 0-7 rulebook + gather, 8 MMA issue, 9 weight loader, 10-13 epilogue.
 #include <algorithm>
 
-#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -33,13 +35,15 @@ namespace sgb {
 
 constexpr int T2_ROWS = 128;
 constexpr int T2_KC = 32;        // channels per iteration (one 128-byte packed line per row)
-constexpr int T2_THREADS = 320;
+constexpr int T2_THREADS = 448;
+constexpr int T2_PROD = 256;    // gather threads (8 warps)
 constexpr int T2_MAXS = 12;      // ring depth limit (barrier arrays)
 constexpr int T2_A_BYTES = T2_ROWS * 128;
 constexpr int kLoShift2 = 11;    // lo = fp16((x - hi) * 2^11): no fp16 subnormals for |x| >= 2^-14
 constexpr float kLoScale2 = (float)(1 << kLoShift2), kLoInv2 = 1.0f / kLoScale2;
 
 struct Tc2Args {
+  const uint32_t *in; int in_stride;     // packed input rows [Min][in_stride words]
   const int32_t *map; int K, Mout, Min;  // map [K][Mout] (nullptr: identity, K == 1)
   const float *Wp;                       // packed weights [K][nkc][4][2][N][8 halves]
   int Cin, N, Cout, NT, nparts;          // N = Cout rounded up to 16; column parts of NT (last may be shorter)
@@ -65,11 +69,6 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-      ::"r"(dst), "l"(tm), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -78,7 +77,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // Shared-memory carve-up (dynamic, 1024-byte aligned): [A ring: S x 16 KB][B ring: S x NT*128 B][map: 2 x K x 128 int32]
-__global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, Tc2Args p) {
+__global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_full[T2_MAXS], bar_empty[T2_MAXS];
   __shared__ __align__(8) unsigned long long bar_accf[2], bar_acce[2], bar_mapf[2], bar_mape[2];
@@ -99,7 +98,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(smem_u32(&bar_full[s]), 5);   // 4 gather warps + the weight loader (each arrive.expect_tx)
+      mbar_init(smem_u32(&bar_full[s]), T2_PROD + 1);  // every gather thread (cp.async ... arrive.noinc) + the weight loader
       mbar_init(smem_u32(&bar_empty[s]), 1);  // tcgen05.commit
     }
     for (int b = 0; b < 2; b++) {
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_mask[0] = s_mask[1] = 0u;
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -123,19 +122,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
 
   const int first = blockIdx.x, stride = gridDim.x;
 
-  if (warp < 4) {
-    // =========================== rulebook slices + TMA gather issue ===========================================
-    const int r = tid;  // tile row owned by this thread for the rulebook
-    int mreg[27];
+  if (warp < 8) {
+    // =========================== rulebook slices + cp.async gather ===========================================
+    const int r = tid & (T2_ROWS - 1);  // tile row this thread reads the rulebook for (two threads per row: even / odd offsets)
+    const int half = tid >> 7;
+    int mreg[14];  // rulebook entries of row r for the offsets half, half + 2, ...
     auto load_map = [&](int item) {  // global -> registers (absent / out of range: -1)
       const int tile = item / p.nparts;
       const int row = tile * T2_ROWS + r;
       const bool ok = row < p.Mout;
       if (p.map) {
 #pragma unroll
-        for (int o = 0; o < 27; o++) mreg[o] = (o < K && ok) ? __ldg(&p.map[(size_t)o * p.Mout + row]) : -1;
+        for (int j = 0; j < 14; j++) {
+          const int o = half + 2 * j;
+          mreg[j] = (o < K && ok) ? __ldg(&p.map[(size_t)o * p.Mout + row]) : -1;
+        }
       } else {
-        mreg[0] = ok ? row : -1;
+        mreg[0] = (ok && half == 0) ? row : -1;
       }
     };
     auto publish_map = [&](int buf, int n) {  // registers -> shared memory, active-offset list, signal
@@ -143,20 +146,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
       int32_t *ms = map_s + (size_t)buf * K * T2_ROWS;
       unsigned int flags = 0u;
 #pragma unroll
-      for (int o = 0; o < 27; o++)
+      for (int j = 0; j < 14; j++) {
+        const int o = half + 2 * j;
         if (o < K) {
-          ms[o * T2_ROWS + r] = (mreg[o] >= 0) ? mreg[o] : p.Min;
-          if (mreg[o] >= 0) flags |= 1u << o;
+          ms[o * T2_ROWS + r] = mreg[j];
+          if (mreg[j] >= 0) flags |= 1u << o;
         }
+      }
       flags = __reduce_or_sync(0xffffffffu, flags);
       if (lane == 0 && flags) atomicOr(&s_mask[buf], flags);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, T2_PROD);
       if (tid < 32) {
         const unsigned int m = s_mask[buf];
         if (tid < K && (m >> tid & 1u)) s_list[buf][__popc(m & ((1u << tid) - 1u))] = tid;
         if (tid == 0) s_nact[buf] = __popc(m);
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, T2_PROD);
       if (tid == 0) {
         s_mask[buf] = 0u;
         mbar_arrive(smem_u32(&bar_mapf[buf]));
@@ -164,9 +169,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
     };
     int n = 0;        // local tile counter
     int g = 0;        // global iteration counter of this CTA (ring position)
-    uint32_t leader;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-    const uint32_t a_base_u = __shfl_sync(0xffffffffu, smem_u32(a_ring), 0);
+    const uint32_t a_base_u = smem_u32(a_ring);
+    // copy geometry of this thread: warp w covers tile rows 16 w .. 16 w + 15 in four instructions of 4 rows x 8 chunks
+    const int sub = lane >> 3, ch = lane & 7;
     if (first < p.items) {
       load_map(first);
       publish_map(0, 0);
@@ -183,27 +188,26 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
         const int s = g % S, u = g / S;
         if (u >= 1) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)((u - 1) & 1));
         const uint32_t bar = smem_u32(&bar_full[s]);
-        if (lane == 0) mbar_expect_tx(bar, 8u * 512u);
-        __syncwarp();
-        // lane j < 8 reads the four rulebook entries of row quad j of this warp; every gather4 is then issued by ONE
-        // elected lane from warp-uniform operands (__shfl_sync broadcasts): issued per lane, each instruction costs an
-        // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~70-120 cycles measured with scripts/tma_probe.cu)
         const int o = s_list[buf][a];
-        int4 rr = make_int4(0, 0, 0, 0);
-        if (lane < 8) rr = *reinterpret_cast<const int4 *>(ms + o * T2_ROWS + warp * 32 + lane * 4);
-        const uint32_t dst0 = a_base_u + (uint32_t)s * T2_A_BYTES + (uint32_t)(warp * 32) * 128u;
-        const int col = kc * T2_KC;
+        const uint32_t stage = a_base_u + (uint32_t)s * T2_A_BYTES;
+        const uint32_t *gcol = p.in + kc * T2_KC + ch * 4;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int r0 = __shfl_sync(0xffffffffu, rr.x, j), r1 = __shfl_sync(0xffffffffu, rr.y, j);
-          const int r2 = __shfl_sync(0xffffffffu, rr.z, j), r3 = __shfl_sync(0xffffffffu, rr.w, j);
-          if (leader) tma_gather4(dst0 + (uint32_t)j * 512u, &tmap, col, r0, r1, r2, r3, bar);
+        for (int j = 0; j < 4; j++) {
+          const int row = warp * 16 + j * 4 + sub;
+          const int src = ms[o * T2_ROWS + row];  // the 8 lanes of a quarter-warp read the same entry (broadcast)
+          const uint32_t dst = stage + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+          const uint32_t *gp = gcol + (size_t)max(src, 0) * p.in_stride;
+          const int nbytes = (src >= 0) ? 16 : 0;  // 0 source bytes = zero fill (absent neighbour)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
         }
+        // the barrier's pending count was initialised with this arrival: it fires when the copies above have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
         if (++kc == nkc) { kc = 0; a++; }
       }
       if (has_next) publish_map(buf ^ 1, n + 1);
     }
-  } else if (warp_u == 4) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp_u == 8) {
     // =========================== MMA issue ====================================================================
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
       for (int i = 0; i < total; i++, g++) {
         const int s = g % S;
         mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((g / S) & 1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async wrote the A stage through the generic proxy
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int ksteps = (min(T2_KC, p.Cin - kc * T2_KC) + 15) >> 4;
         uint64_t ad = desc_sw128(a_base + (uint32_t)s * T2_A_BYTES);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =========================== weight loader ================================================================
     int n = 0, g = 0;
     uint32_t leader;
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
       }
     }
   } else {
-    // =========================== epilogue (warps 6-9; TMEM lane group = warp % 4) ==============================
+    // =========================== epilogue (warps 10-13; TMEM lane group = warp % 4) ============================
     const int lg = warp & 3;
     int n = 0;
     for (int item = first; item < p.items; item += stride, n++) {
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_tma_kernel(const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
@@ -440,22 +445,6 @@ __global__ void act_pack_kernel(const float *__restrict__ x, int x_stride, int x
   uint32_t *yr = y + (size_t)row * y_stride + (ch >> 5) * 32 + ((ch & 31) >> 1);
   yr[0] = *reinterpret_cast<const uint32_t *>(&h);
   yr[16] = *reinterpret_cast<const uint32_t *>(&l);
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn tmap_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)f;
-  }
-  return fn;
 }
 
 static int *g_oflow = nullptr;  // device flag shared by every launch of this process (per current device at first use)
@@ -503,13 +492,13 @@ int sgb_act_pack(const float *d_x, int x_stride, int x_off, const float *d_scale
   return SGB_OK;
 }
 
-int sgb_spconv_forward_tma(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
+int sgb_spconv_forward_ss(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
                            const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
                            const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
                            int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill, void *stream) {
   if (Mout == 0 || Cout == 0) return SGB_OK;
   SGB_REQUIRE(d_in_pk && d_Wp && (d_out || d_pk_out) && K >= 1 && K <= 27 && Mout > 0 && Min > 0 && Cin > 0 && Cout > 0, SGB_ERR_ARG,
-              "spconv_forward_tma arguments");
+              "spconv_forward_ss arguments");
   SGB_REQUIRE(d_map || (K == 1 && Min >= Mout), SGB_ERR_ARG, "identity map requires K == 1");
   SGB_REQUIRE((in_stride & 31) == 0 && in_stride >= (Cin + 31) / 32 * 32, SGB_ERR_ARG, "packed input row stride (words, multiple of 32)");
   SGB_REQUIRE((((uintptr_t)d_in_pk) & 15) == 0, SGB_ERR_ARG, "packed input must be 16-byte aligned");
@@ -518,24 +507,11 @@ int sgb_spconv_forward_tma(const float *d_in_pk, int in_stride, int Min, const i
               "packed output: row stride multiple of 32 words, channel offset multiple of 8");
   SGB_REQUIRE((d_pk_scale == nullptr) == (d_pk_shift == nullptr), SGB_ERR_ARG, "scale/shift must come together");
   const int N = (Cout + 15) / 16 * 16;
-  SGB_REQUIRE(N <= 256 && Cin <= 512, SGB_ERR_RANGE, "spconv_forward_tma: Cout > 256 or Cin > 512 is not tiled");
+  SGB_REQUIRE(N <= 256 && Cin <= 512, SGB_ERR_RANGE, "spconv_forward_ss: Cout > 256 or Cin > 512 is not tiled");
   int rc = ensure_oflow();
   if (rc) return rc;
-  EncodeTiledFn enc = tmap_encoder();
-  SGB_REQUIRE(enc, SGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  CUtensorMap tm;
-  {
-    // rows = Min: index Min ("absent neighbour") is out of bounds and zero-filled by the TMA unit
-    cuuint64_t dims[2] = {(cuuint64_t)in_stride, (cuuint64_t)Min};
-    cuuint64_t strides[1] = {(cuuint64_t)in_stride * 4};
-    cuuint32_t box[2] = {32, 1};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)d_in_pk, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SGB_REQUIRE(r == CUDA_SUCCESS, SGB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  }
   Tc2Args p;
+  p.in = (const uint32_t *)d_in_pk; p.in_stride = in_stride;
   p.map = d_map; p.K = K; p.Mout = Mout; p.Min = Min;
   p.Wp = d_Wp; p.Cin = Cin; p.N = N; p.Cout = Cout;
   p.residual = d_residual; p.res_stride = res_stride; p.res_off = res_off;
@@ -568,11 +544,11 @@ int sgb_spconv_forward_tma(const float *d_in_pk, int in_stride, int Min, const i
   const size_t smem = (size_t)S * (T2_A_BYTES + b_stage) + map_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(spconv_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   const int grid = std::min(p.items, sms);
-  spconv_tma_kernel<<<grid, T2_THREADS, smem, (cudaStream_t)stream>>>(tm, p);
+  spconv_ss_kernel<<<grid, T2_THREADS, smem, (cudaStream_t)stream>>>(p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -302,12 +302,12 @@ class SoftGroup(nn.Module):
             output = self.output_layer(self.unet(self.input_conv(input)))
             output_feats = output.features  # stays on voxel rows (softgroup.py:373-374)
         else:
-            output = self.input_conv(input)
-            output = self.unet(output)
-            output = self.output_layer(output)
             from ..ops import _lib
             from ..ops._lib import check, ptr
             import ctypes
+            output = self.input_conv(input)
+            output = self.unet(output)
+            output = self.output_layer(output)
             vf = output.features
             N = input_map.size(0)
             output_feats = torch.empty((N, vf.size(1)), dtype=vf.dtype, device=vf.device)

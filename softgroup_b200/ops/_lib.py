@@ -59,7 +59,7 @@ SIGNATURES = {
     'sgb_spconv_lo_shift': (c_int, []),
     'sgb_spconv_overflow': (c_int, [_INTP, _P]),
     'sgb_act_pack': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    'sgb_spconv_forward_tma': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
+    'sgb_spconv_forward_ss': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
                                        c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),

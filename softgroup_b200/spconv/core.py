@@ -166,8 +166,8 @@ def pack_weight_tc(W, lo_shift=None):
 
 class WeightPack(object):
     """Weight of one conv in the kernels' formats: .kio [K,Cin,Cout] (CUDA-core kernel), .tc() the packed fp16 hi/lo
-    split of the round-1 tcgen05 kernel, .tma() the same split with the remainder scaled by 2^sgb_spconv_lo_shift() for
-    the TMA-gather kernel."""
+    split of the round-1 tcgen05 kernel, .ss() the same split with the remainder scaled by 2^sgb_spconv_lo_shift() for
+    the round-2 kernel (spconv_ss.cu)."""
     __slots__ = ('kio', 'packed', 'packed2')
 
     def __init__(self, kio):
@@ -180,7 +180,7 @@ class WeightPack(object):
             self.packed = pack_weight_tc(self.kio)
         return self.packed
 
-    def tma(self):
+    def ss(self):
         if self.packed2 is None:
             self.packed2 = pack_weight_tc(self.kio, lo_shift=_lib.lib().sgb_spconv_lo_shift())
         return self.packed2
@@ -223,16 +223,16 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    use_tc = CONV_IMPL in ('tc', 'tma') and Cout <= 256 and Cin <= 512
+    use_tc = CONV_IMPL in ('tc', 'ss') and Cout <= 256 and Cin <= 512
     name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
-    if use_tc and CONV_IMPL == 'tma':
-        name = 'spconv_tma_kernel' + ('' if mp is not None else '(1x1/linear)')
+    if use_tc and CONV_IMPL == 'ss':
+        name = 'spconv_ss_kernel' + ('' if mp is not None else '(1x1/linear)')
         pk = act_pack(feats, in_stride, in_off, Cin, act=act, relu=act is not None)
         with profiler.record(name, nbytes):
             check(
-                _lib.lib().sgb_spconv_forward_tma(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.tma()), Cin, Cout,
+                _lib.lib().sgb_spconv_forward_ss(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.ss()), Cin, Cout,
                                                   ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride, out_off, None, 0,
-                                                  0, None, None, 0, 0, _stream()), 'sgb_spconv_forward_tma')
+                                                  0, None, None, 0, 0, _stream()), 'sgb_spconv_forward_ss')
         return out
     if use_tc:
         # activation (+ split into fp16 hi/lo) once per tensor instead of once per gathered (row, offset) in the conv
