@@ -40,6 +40,9 @@ class SparseConvTensor(object):
         self.batch_size = batch_size
         self.indice_dict = indice_dict if indice_dict is not None else {}
         self.grid = grid
+        # packed (activated + fp16 hi/lo split) versions of `features`, keyed by the consumer BatchNorm module whose
+        # (scale, shift, ReLU) they were produced with; filled by producing convs (Emit), read by consuming convs
+        self.packed = {}
 
     def replace_feature(self, feature):
         out = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid,
@@ -207,33 +210,55 @@ def act_pack(feats, in_stride, in_off, C, act=None, relu=None, out=None, out_cof
     return out
 
 
+class Emit(object):
+    """What a producing conv writes besides (or instead of) fp32 rows: the packed rows of ITS CONSUMER's input, i.e.
+    relu(y * scale + shift) split into fp16 hi/lo -- the consumer's BatchNorm(eval)+ReLU folded into this epilogue.
+    key: the consumer's BatchNorm module (identity of the activation); buf/coff: existing packed buffer + channel offset
+    (concat halves) or None for a fresh one; fill: zero the unused half of a last 32-channel chunk."""
+    __slots__ = ('scale', 'shift', 'key', 'buf', 'coff', 'fill')
+
+    def __init__(self, scale, shift, key, buf=None, coff=0, fill=True):
+        self.scale, self.shift, self.key, self.buf, self.coff, self.fill = scale, shift, key, buf, coff, fill
+
+
 def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, residual=None, bias=None, out=None,
-                 out_stride=None, out_off=0):
-    """Thin wrapper over sgb_spconv_forward_tc / sgb_spconv_forward. W: WeightPack or [K, Cin, Cout] f32 tensor.
-    act: (scale, shift) or None."""
-    if out is None:
-        out = torch.empty((Mout, Cout), dtype=torch.float32, device=feats.device)
-        out_stride = Cout
+                 out_stride=None, out_off=0, packed_in=None, emit=None, want_fp32=True, m_in=None):
+    """Thin wrapper over sgb_spconv_forward_ss / _tc / sgb_spconv_forward. W: WeightPack or [K, Cin, Cout] f32 tensor.
+    act: (scale, shift) or None. Round-2 kernel only: packed_in = the input already activated + packed (feats may then be
+    None, m_in = its row count); emit = Emit(...) makes the epilogue write the consumer's packed input; want_fp32 = False
+    skips the fp32 rows (single-consumer intermediates). Returns the fp32 tensor (or None); with emit, (fp32, packed)."""
     if not isinstance(W, WeightPack):
         W = WeightPack(W)
+    use_tc = CONV_IMPL in ('tc', 'ss') and Cout <= 256 and Cin <= 512
+    fused = use_tc and CONV_IMPL == 'ss'
+    assert fused or (packed_in is None and emit is None and want_fp32), 'packed I/O needs the round-2 conv kernel'
+    if out is None and want_fp32:
+        out = torch.empty((Mout, Cout), dtype=torch.float32, device=(feats if feats is not None else packed_in).device)
+        out_stride = Cout
     scale, shift = act if act is not None else (None, None)
     rs, ro = (residual.stride(0), 0) if residual is not None else (0, 0)
     # algorithmic bytes (SURVEY.md 8d): input rows once + weights + map + output rows (+ residual)
-    m_in = feats.size(0)
+    if m_in is None:
+        m_in = feats.size(0)
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    use_tc = CONV_IMPL in ('tc', 'ss') and Cout <= 256 and Cin <= 512
     name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
-    if use_tc and CONV_IMPL == 'ss':
+    if fused:
         name = 'spconv_ss_kernel' + ('' if mp is not None else '(1x1/linear)')
-        pk = act_pack(feats, in_stride, in_off, Cin, act=act, relu=act is not None)
+        pk = packed_in if packed_in is not None else act_pack(feats, in_stride, in_off, Cin, act=act, relu=act is not None)
+        pk_out, pk_stride, pk_coff, es, eh, fill = None, 0, 0, None, None, 0
+        if emit is not None:
+            if emit.buf is None:
+                emit.buf = torch.empty((Mout, (Cout + 31) // 32 * 32), dtype=torch.float32, device=pk.device)
+            pk_out, pk_stride, pk_coff, es, eh, fill = emit.buf, emit.buf.size(1), emit.coff, emit.scale, emit.shift, int(emit.fill)
         with profiler.record(name, nbytes):
             check(
                 _lib.lib().sgb_spconv_forward_ss(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.ss()), Cin, Cout,
-                                                  ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride, out_off, None, 0,
-                                                  0, None, None, 0, 0, _stream()), 'sgb_spconv_forward_ss')
-        return out
+                                                 ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride or 0, out_off,
+                                                 ptr(pk_out), pk_stride, pk_coff, ptr(es), ptr(eh), 1, fill, _stream()),
+                'sgb_spconv_forward_ss')
+        return (out, pk_out) if emit is not None else out
     if use_tc:
         # activation (+ split into fp16 hi/lo) once per tensor instead of once per gathered (row, offset) in the conv
         K_eff = K
@@ -304,42 +329,60 @@ class _SparseConvBase(SparseModule):
             self._wt = (ver, WeightPack(w.float()))
         return self._wt[1]
 
-    def _features(self, x):
+    def _features(self, x, fuse=None):
         f = x.features
+        if f is None:  # a packed-only intermediate (its producer skipped the fp32 rows): the caller hands the packed input
+            assert fuse is not None and fuse.get('packed_in') is not None, 'features exist only in packed form'
+            return None
         assert f.is_cuda and f.dtype == torch.float32, 'softgroup_b200 sparse convs run on CUDA float32 features'
         if f.stride(-1) != 1:
             f = f.contiguous()
         return f
 
 
+def _stride0(f):
+    return f.stride(0) if f is not None else 0
+
+
+def _wrap(t, o, fuse):
+    """conv_forward result -> SparseConvTensor: fp32 rows (possibly None) + the packed rows emitted for the consumer."""
+    emit = fuse.get('emit') if fuse else None
+    if emit is not None:
+        o, pk = o
+        t.packed[emit.key] = pk
+    t.features = o
+    return t
+
+
 class SubMConv3d(_SparseConvBase):
     """Submanifold 3x3x3 convolution (blocks.py:57-70, softgroup.py:61)."""
 
-    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0):
+    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0, **fuse):
         assert self.kernel_size == [3, 3, 3], 'only the k=3 submanifold conv of the reference is built'
-        f = self._features(x)
+        f = self._features(x, fuse)
         rb = x.find_indice_pair(self.indice_key)
         if rb is None:
             rb = {'kind': 'subm', 'map': build_subm_map(x.indices)}
             if self.indice_key is not None:
                 x.indice_dict[self.indice_key] = rb
         M = x.indices.size(0)
-        o = conv_forward(f, f.stride(0), 0, rb['map'], 27, M, self.weight_kio(), self.in_channels, self.out_channels,
-                         act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride, out_off=out_off)
-        return x.replace_feature(o)
+        o = conv_forward(f, _stride0(f), 0, rb['map'], 27, M, self.weight_kio(), self.in_channels, self.out_channels,
+                         act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride, out_off=out_off,
+                         m_in=M, **fuse)
+        return _wrap(x.replace_feature(None), o, fuse)
 
 
 class SparseConv3d(_SparseConvBase):
     """k=2 s=2 strided sparse conv (blocks.py:101-107) and, with kernel_size=1, the dense 1x1 (blocks.py:31-41)."""
 
-    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0):
-        f = self._features(x)
+    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0, **fuse):
+        f = self._features(x, fuse)
         if self.kernel_size == [1, 1, 1]:
             M = x.indices.size(0)
-            o = conv_forward(f, f.stride(0), 0, None, 1, M, self.weight_kio(), self.in_channels, self.out_channels,
+            o = conv_forward(f, _stride0(f), 0, None, 1, M, self.weight_kio(), self.in_channels, self.out_channels,
                              act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride,
-                             out_off=out_off)
-            return x.replace_feature(o)
+                             out_off=out_off, m_in=M, **fuse)
+            return _wrap(x.replace_feature(None), o, fuse)
         assert self.kernel_size == [2, 2, 2] and self.stride == [2, 2, 2] and self.padding == [0, 0, 0], \
             'only the k2 s2 p0 strided conv of the reference is built'
         rb = x.find_indice_pair(self.indice_key)
@@ -350,10 +393,11 @@ class SparseConv3d(_SparseConvBase):
             if self.indice_key is not None:
                 x.indice_dict[self.indice_key] = rb
         Mout = rb['out_indices'].size(0)
-        o = conv_forward(f, f.stride(0), 0, rb['map'], 8, Mout, self.weight_kio(), self.in_channels, self.out_channels,
-                         act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride, out_off=out_off)
-        t = SparseConvTensor(o, rb['out_indices'], rb['out_shape'], x.batch_size, x.grid, x.indice_dict)
-        return t
+        o = conv_forward(f, _stride0(f), 0, rb['map'], 8, Mout, self.weight_kio(), self.in_channels, self.out_channels,
+                         act=act, residual=residual, bias=self.bias, out=out, out_stride=out_stride, out_off=out_off,
+                         m_in=x.indices.size(0), **fuse)
+        t = SparseConvTensor(None, rb['out_indices'], rb['out_shape'], x.batch_size, x.grid, x.indice_dict)
+        return _wrap(t, o, fuse)
 
 
 class SparseInverseConv3d(_SparseConvBase):
@@ -407,48 +451,88 @@ class SparseSequential(SparseModule):
 
     @staticmethod
     def _flush(x, pending):
-        scale, shift, relu = pending
+        scale, shift, relu = pending[:3]
         if isinstance(x, SparseConvTensor):
             return x.replace_feature(bn_relu_rows(x.features, scale, shift, relu))
         return bn_relu_rows(x, scale, shift, relu)
 
-    def forward(self, input, residual=None, out=None, out_stride=None, out_off=0):
-        """residual / out* apply to the LAST sparse conv of the sequence (fused epilogue)."""
+    def forward(self, input, residual=None, out=None, out_stride=None, out_off=0, next_act=None, emit_buf=None):
+        """residual / out* apply to the LAST sparse conv of the sequence (fused epilogue).
+
+        Round-2 kernel (CONV_IMPL == 'ss'): activations travel PACKED between convolutions. A conv followed inside this
+        sequence by BatchNorm+ReLU+conv writes only the packed rows its successor reads (that BatchNorm+ReLU folded into
+        its epilogue, no fp32 rows at all); `next_act` = the BatchNorm module that will consume this sequence's OUTPUT
+        (behind a ReLU, in front of a conv) makes the last conv emit those packed rows next to its fp32 rows, into
+        `emit_buf` = (packed buffer, channel offset, scale, shift) when the consumer reads a concat buffer. Child
+        modules that take the same hint (ResidualBlock) are chained the same way."""
         mods = list(self._modules.values())
-        last_conv = max([i for i, m in enumerate(mods) if isinstance(m, _SparseConvBase)], default=-1)
-        pending = None  # (scale, shift, relu)
+        conv_idx = [i for i, m in enumerate(mods) if isinstance(m, _SparseConvBase)]
+        last_conv = conv_idx[-1] if conv_idx else -1
+        fused = CONV_IMPL == 'ss'
+        pending = None  # (scale, shift, relu, bn module)
+        carry = None    # packed input prepared by the previous conv of this sequence for exactly `pending`
         x = input
         for i, m in enumerate(mods):
             is_sparse_in = isinstance(x, SparseConvTensor)
             feats = x.features if is_sparse_in else x
-            fusable = feats.is_cuda and feats.dtype == torch.float32
+            fusable = feats is None or (feats.is_cuda and feats.dtype == torch.float32)
             if isinstance(m, nn.BatchNorm1d) and fusable and not m.training:
                 if pending is not None:
                     x = self._flush(x, pending)
                 s, b = fold_bn(m)
-                pending = (s, b, False)
+                pending = (s, b, False, m)
                 continue
             if isinstance(m, nn.ReLU) and pending is not None and not pending[2]:
-                pending = (pending[0], pending[1], True)
+                pending = (pending[0], pending[1], True, pending[3])
                 continue
             if isinstance(m, _SparseConvBase):
-                act = None
+                act, fuse = None, {}
                 if pending is not None:
                     if pending[2]:
                         act = (pending[0], pending[1])
+                        if fused and is_sparse_in:
+                            pk = carry if carry is not None else x.packed.get(pending[3])
+                            if pk is not None:
+                                fuse['packed_in'] = pk
                     else:  # BN without ReLU in front of a conv: not fusable into the relu'd input transform
                         x = self._flush(x, pending)
                     pending = None
+                carry = None
+                if fused and is_sparse_in and m.out_channels <= 256 and m.in_channels <= 512:
+                    nxt = mods[i + 1:i + 4]
+                    if (len(nxt) == 3 and isinstance(nxt[0], nn.BatchNorm1d) and not nxt[0].training and
+                            isinstance(nxt[1], nn.ReLU) and isinstance(nxt[2], _SparseConvBase) and i != last_conv):
+                        es, eb = fold_bn(nxt[0])
+                        fuse['emit'] = Emit(es, eb, nxt[0])
+                        fuse['want_fp32'] = False  # the intermediate never leaves this sequence
+                    elif i == last_conv and emit_buf is not None:
+                        buf, coff, es, eb, key = emit_buf
+                        fuse['emit'] = Emit(es, eb, key, buf=buf, coff=coff, fill=False)
+                    elif i == last_conv and next_act is not None and i == len(mods) - 1:
+                        es, eb = fold_bn(next_act)
+                        fuse['emit'] = Emit(es, eb, next_act)
                 if i == last_conv:
-                    x = m(x, act=act, residual=residual, out=out, out_stride=out_stride, out_off=out_off)
+                    x = m(x, act=act, residual=residual, out=out, out_stride=out_stride, out_off=out_off, **fuse)
                 else:
-                    x = m(x, act=act)
+                    x = m(x, act=act, **fuse)
+                if 'emit' in fuse and not fuse.get('want_fp32', True):
+                    carry = x.packed[fuse['emit'].key]
                 continue
             if pending is not None:
                 x = self._flush(x, pending)
                 pending = None
             if isinstance(m, SparseModule):
-                x = m(x)
+                if fused and getattr(m, 'takes_next_act', False):
+                    # chain blocks: the consumer of this block's output is the first BatchNorm of the next block, or the
+                    # consumer named by our caller when this is the last module
+                    hint = None
+                    if i + 1 < len(mods) and getattr(mods[i + 1], 'takes_next_act', False):
+                        hint = mods[i + 1].first_norm()
+                    elif i == len(mods) - 1:
+                        hint = next_act
+                    x = m(x, next_act=hint)
+                else:
+                    x = m(x)
             elif isinstance(x, SparseConvTensor):
                 if isinstance(m, nn.Identity):
                     continue

@@ -46,7 +46,8 @@ def _pair(ref_module, cfg, calibrated=None, scan=None):
     ours = ours.cuda()
     if calibrated is None:
         harness.calibrate_heads(ours, harness.to_host_batch(scan))
-    ref = ref_module.SoftGroup(**cfg).eval()
+    ref = ref_module.SoftGroup(**cfg)
+    ref.eval()  # the reference overrides train() without returning self (softgroup.py:98-104): no chaining
     ref.load_state_dict(ours.state_dict(), strict=True)  # identical names and shapes: checkpoints load unchanged
     return ours, ref.cuda()
 
