@@ -203,54 +203,41 @@ int sgb_spconv_forward(const float *d_in, int in_stride, int in_off, const int32
                        const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
                        int out_stride, int out_off, void *stream);
 
-/* Tensor-core version of sgb_spconv_forward (tcgen05.mma kind::f16, fp32 accumulators in TMEM). Every operand value x
- * is carried as two fp16 numbers hi = fp16(x), lo = fp16(x - hi) and the product is hi*hi + hi*lo + lo*hi, so results
- * are fp32-grade. Same semantics as sgb_spconv_forward; Cin <= 512, Cout <= 256. Weights come
- * pre-split and pre-packed in ONE array (softgroup_b200/spconv/core.py:pack_weight_tc):
- *   N = Cout rounded up to 16, nkc = ceil(Cin/32);
- *   Wp fp16 [K][nkc][4][2][N][8]: element (k, kc, q, part, n, e) = part(W[k][32*kc + 8*q + e][n]) (0 outside Cin/Cout),
- *   part 0 = hi, part 1 = lo -- i.e. per (k, kc) a UMMA K-major / no-swizzle operand [B_hi | B_lo] of 16-byte chunks.
- *   The array is passed as float* (two halves per 32-bit word); sgb_spconv_tc_packed_floats returns its length in words.
- * in_packed != 0: d_in holds rows already activated and split by sgb_act_split (d_in_scale/d_in_shift must be NULL,
- * in_stride and in_off multiples of 32 words). */
-long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout);
-/* log2 of the factor the fp16 remainders are carried with: lo = fp16((x - hi) * 2^shift) for weights (host packer) and
- * activations (sgb_act_split / in-kernel split); the kernel scales the correction products back. 0 in this build. */
-int sgb_spconv_tc_lo_shift(void);
-int sgb_spconv_forward_tc(const float *d_in, int in_stride, int in_off, const int32_t *d_map, int K, int Mout,
-                          const float *d_Wp, int Cin, int Cout, const float *d_in_scale, const float *d_in_shift,
-                          const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
-                          int out_stride, int out_off, int in_packed, void *stream);
-/* Activation + split, once per tensor instead of once per gathered (row, offset): y = relu?(x*scale+shift) (or x when
- * scale is NULL) written as packed fp16 hi/lo words, d_y f32-typed [M, ceil(C/32)*32]: per 32-channel chunk 16 words of
- * hi pairs then 16 words of lo pairs. Feed to sgb_spconv_forward_tc with in_packed = 1 (in_stride = ceil(C/32)*32). */
-int sgb_act_split(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
-                  float *d_y, int M, int C, void *stream);
-
 /* ---------------------------------------------------------------------------------------------
- * Round-2 sparse convolution (spconv_ss.cu): same contraction as sgb_spconv_forward_tc; input rows of PACKED activations
- * gathered by a deep cp.async ring straight into the swizzled shared-memory operand of tcgen05.mma, persistent CTAs,
- * accumulators double-buffered in tensor memory, fused output packing.
- * Packed rows: per 32-channel chunk 16 words of fp16 hi pairs then 16 words of fp16 lo pairs, x = hi + lo * 2^-shift with
- * shift = sgb_spconv_lo_shift() (weights packed by the host with the same shift: [K][nkc][4][2][N][8 halves]).
- *   d_in_pk [Min rows][in_stride words]; rulebook entry -1 = no neighbour (zero row).
- *   outputs (either or both): d_out fp32 rows (strided like sgb_spconv_forward_tc); d_pk_out packed rows written at
- *   channel offset pk_coff (multiple of 8) after y = relu?(x * pk_scale[c] + pk_shift[c]) per OUTPUT channel c -- the
- *   consumer's BatchNorm(eval)+ReLU folded into this producer; pk_fill != 0 also zeroes the upper half of a last chunk
- *   that N = Cout rounded to 16 leaves half written.
- * sgb_act_pack: the same packing for tensors without a producing convolution (C real channels, zero up to Cfill).
- * sgb_spconv_overflow: a packed value beyond the fp16 range (|y| > 65504, or NaN) raises a device flag instead of
- * saturating silently; this call reads and clears it (blocking 4-byte read).
+ * Tensor-core sparse convolution (spconv_tc.cu; tcgen05.mma kind::f16, fp32 accumulators in TMEM) -- the production path
+ * for Cin <= 512, Cout <= 256. Every operand value x is carried as two fp16 numbers hi = fp16(x),
+ * lo = fp16((x - hi) * 2^shift), shift = sgb_spconv_lo_shift(), and the product is hi*hi + hi*lo + lo*hi: fp32-grade
+ * (DESIGN.md 3.2). Activations travel PACKED between convolutions: per row and 32-channel chunk 16 words of fp16 hi pairs
+ * then 16 words of fp16 lo pairs (one 128-byte line), float32-typed buffers [rows][ceil(C/32)*32 words].
+ *   Weights, pre-split and pre-packed by the host (softgroup_b200/spconv/core.py:pack_weight_tc) with the same shift:
+ *     N = Cout rounded up to 16, nkc = ceil(Cin/32);
+ *     Wp fp16 [K][nkc][4][2][N][8]: element (k, kc, q, part, n, e) = part(W[k][32*kc + 8*q + e][n]) (0 outside Cin/Cout),
+ *     part 0 = hi, part 1 = lo -- per (k, kc) a UMMA K-major / no-swizzle operand [B_hi | B_lo] of 16-byte chunks;
+ *     passed as float* (two halves per word); sgb_spconv_tc_packed_floats = its length in words.
+ *   sgb_spconv_forward_tc: d_in_pk packed input [Min][in_stride words] ALREADY activated (the consumer's
+ *     BatchNorm(eval)+ReLU was applied by whoever packed it); d_map int32 [K][Mout] (-1 = no neighbour) or NULL for the
+ *     identity (K == 1: 1x1 conv / nn.Linear). Outputs, either or both: d_out fp32 rows (strided: concat buffers);
+ *     d_pk_out packed rows at channel offset pk_coff (multiple of 8) after y = relu?(x * pk_scale[c] + pk_shift[c]) per
+ *     OUTPUT channel c -- the NEXT layer's BatchNorm(eval)+ReLU folded into this producer (an intermediate with a single
+ *     consumer never exists in fp32); pk_fill != 0 also zeroes the upper half of a last chunk that N leaves half written.
+ *   sgb_act_pack: the same packing for tensors without a producing convolution (C real channels, zeros up to Cfill).
+ *   sgb_spconv_overflow: a packed value beyond the fp16 range (|y| > 65504, or NaN) raises a per-device flag instead of
+ *     saturating silently; this call reads and clears it (blocking 4-byte read on `stream`).
+ *   sgb_spconv_tc_plan: the tile configuration the launch uses for a problem size (pure function; sms <= 0: 148):
+ *     out[0] = NT (columns per CTA), [1] = column parts, [2] = split-K cluster size, [3] = TMEM columns per CTA,
+ *     [4] = pipeline stages, [5] = row tiles.
  * ------------------------------------------------------------------------------------------- */
+long long sgb_spconv_tc_packed_floats(int K, int Cin, int Cout);
 int sgb_spconv_lo_shift(void);
 int sgb_spconv_overflow(int *h_flag, void *stream);
+int sgb_spconv_tc_plan(int K, int Mout, int Cin, int Cout, int has_map, int sms, int *out);
 int sgb_act_pack(const float *d_x, int x_stride, int x_off, const float *d_scale, const float *d_shift, int relu,
                  float *d_pk, int pk_stride, int pk_coff, int M, int C, int Cfill, void *stream);
-int sgb_spconv_forward_ss(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
-                           const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
-                           const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
-                           int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill,
-                           void *stream);
+int sgb_spconv_forward_tc(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
+                          const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
+                          const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
+                          int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill,
+                          void *stream);
 
 /* y[i, c] = max(x[i, c]*scale[c] + shift[c], 0) (relu != 0) -- BatchNorm1d(eval)+ReLU over rows. */
 int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const float *d_shift, int relu, float *d_y,

@@ -1,5 +1,5 @@
-"""Per-level timing of one SubM 3x3x3 convolution (C_l -> C_l) on the rulebooks of the 150k-point bench scan, for the
-conv implementations named on the command line (default: tc ss). L2 is flushed before every timed launch; the packed
+"""Per-level timing of one SubM 3x3x3 convolution (C_l -> C_l) on the rulebooks of the 150k-point bench scan (tcgen05
+kernel; --morton puts the rows in Z-order first). L2 is flushed before every timed launch; the packed
 input is prepared outside the timed region so the number is the conv kernel alone.
 Usage: python scripts/conv_levels_ab.py [impl ...]"""
 import sys
@@ -13,7 +13,7 @@ from softgroup_b200.spconv import core  # noqa: E402
 from softgroup_b200.ops import _lib  # noqa: E402
 from softgroup_b200.ops._lib import check, ptr  # noqa: E402
 
-impls = [a for a in sys.argv[1:] if not a.startswith('--')] or ['tc', 'ss']
+impls = ['tc']
 ORDER = 'morton' if '--morton' in sys.argv else 'orig'
 
 
@@ -54,19 +54,11 @@ for lvl, C, M, mp in levels:
     outs = {}
     for impl in impls:
         out = torch.empty(M, C, device='cuda')
-        if impl == 'tc':
-            pk = torch.empty((M, C), dtype=torch.float32, device='cuda')
-            check(L.sgb_act_split(ptr(x), C, 0, None, None, 1, ptr(pk), M, C, core._stream()))
+        pk = core.act_pack(x, C, 0, C)
 
-            def run():
-                check(L.sgb_spconv_forward_tc(ptr(pk), C, 0, ptr(mp), 27, M, ptr(W.tc()), C, C, None, None, None, 0, 0, None,
-                                              ptr(out), C, 0, 1, core._stream()))
-        else:
-            pk = core.act_pack(x, C, 0, C)
-
-            def run():
-                check(L.sgb_spconv_forward_ss(ptr(pk), C, M, ptr(mp), 27, M, ptr(W.ss()), C, C, None, 0, 0, None, ptr(out), C, 0,
-                                               None, 0, 0, None, None, 0, 0, core._stream()))
+        def run():
+            check(L.sgb_spconv_forward_tc(ptr(pk), C, M, ptr(mp), 27, M, ptr(W.tc()), C, C, None, 0, 0, None, ptr(out), C, 0,
+                                          None, 0, 0, None, None, 0, 0, core._stream()))
         for _ in range(2):
             run()
         ts = []

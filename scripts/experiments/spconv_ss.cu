@@ -33,6 +33,18 @@
 
 namespace sgb {
 
+#ifdef SGB_SS_TIMELINE
+#define TL_DECL long long tl_acc = 0, tl_t0 = 0; const bool tl_on = p.dbg && blockIdx.x == 0 && lane == 0
+#define TL_BEGIN() do { if (tl_on) tl_t0 = clock64(); } while (0)
+#define TL_END() do { if (tl_on) tl_acc += clock64() - tl_t0; } while (0)
+#define TL_STORE(slot) do { if (tl_on) p.dbg[slot] = tl_acc; } while (0)
+#else
+#define TL_DECL
+#define TL_BEGIN()
+#define TL_END()
+#define TL_STORE(slot)
+#endif
+
 constexpr int T2_ROWS = 128;
 constexpr int T2_KC = 32;        // channels per iteration (one 128-byte packed line per row)
 constexpr int T2_THREADS = 448;
@@ -56,6 +68,7 @@ struct Tc2Args {
   int *oflow;                            // device flag: |value| > 65504 met while packing
   int S;                                 // ring stages
   int tiles, items;
+  long long *dbg;                        // SGB_SS_TIMELINE builds only: per-role wait/busy cycle counters of CTA 0
 };
 
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {  // K-major SWIZZLE_128B, 8-row groups 1024 B apart
@@ -169,6 +182,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
     };
     int n = 0;        // local tile counter
     int g = 0;        // global iteration counter of this CTA (ring position)
+    TL_DECL;
+#ifdef SGB_SS_TIMELINE
+    long long tl_pub = 0, tl_start = clock64();
+#endif
     const uint32_t a_base_u = smem_u32(a_ring);
     // copy geometry of this thread: warp w covers tile rows 16 w .. 16 w + 15 in four instructions of 4 rows x 8 chunks
     const int sub = lane >> 3, ch = lane & 7;
@@ -186,7 +203,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
       int a = 0, kc = 0;
       for (int i = 0; i < total; i++, g++) {
         const int s = g % S, u = g / S;
+        TL_BEGIN();
         if (u >= 1) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)((u - 1) & 1));
+        TL_END();
         const uint32_t bar = smem_u32(&bar_full[s]);
         const int o = s_list[buf][a];
         const uint32_t stage = a_base_u + (uint32_t)s * T2_A_BYTES;
@@ -204,24 +223,49 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
         if (++kc == nkc) { kc = 0; a++; }
       }
+#ifdef SGB_SS_TIMELINE
+      const long long tp0 = clock64();
+#endif
       if (has_next) publish_map(buf ^ 1, n + 1);
+#ifdef SGB_SS_TIMELINE
+      tl_pub += clock64() - tp0;
+#endif
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+#ifdef SGB_SS_TIMELINE
+    if (tl_on && warp == 0) { p.dbg[0] = clock64() - tl_start; p.dbg[1] = tl_acc; p.dbg[2] = tl_pub; p.dbg[9] = g; p.dbg[10] = n; }
+#endif
   } else if (warp_u == 8) {
     // =========================== MMA issue ====================================================================
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
     int n = 0, g = 0;
+    TL_DECL;
+#ifdef SGB_SS_TIMELINE
+    long long tl_acce = 0, tl_mapf = 0;
+#endif
     for (int item = first; item < p.items; item += stride, n++) {
       const int buf = n & 1, ab = n & 1;
       const int part = item % p.nparts;
       const int nt = min(NT, p.N - part * NT);
+#ifdef SGB_SS_TIMELINE
+      long long tq = clock64();
+#endif
       mbar_wait(smem_u32(&bar_mapf[buf]), (uint32_t)((n >> 1) & 1));
+#ifdef SGB_SS_TIMELINE
+      tl_mapf += clock64() - tq;
+#endif
       const int total = __shfl_sync(0xffffffffu, s_nact[buf], 0) * nkc;
       __syncwarp();
       if (leader) mbar_arrive(smem_u32(&bar_mape[buf]));
+#ifdef SGB_SS_TIMELINE
+      tq = clock64();
+#endif
       if (n >= 2) mbar_wait(smem_u32(&bar_acce[ab]), (uint32_t)(((n >> 1) - 1) & 1));
+#ifdef SGB_SS_TIMELINE
+      tl_acce += clock64() - tq;
+#endif
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d = tmem + (uint32_t)(ab * acc_cols);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * nt) >> 3) << 17) | ((uint32_t)(T2_ROWS >> 4) << 24);
@@ -232,7 +276,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
       int kc = 0;
       for (int i = 0; i < total; i++, g++) {
         const int s = g % S;
+        TL_BEGIN();
         mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((g / S) & 1));
+        TL_END();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async wrote the A stage through the generic proxy
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int ksteps = (min(T2_KC, p.Cin - kc * T2_KC) + 15) >> 4;
@@ -257,6 +303,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
       }
       __syncwarp();
     }
+#ifdef SGB_SS_TIMELINE
+    if (tl_on) { p.dbg[3] = tl_acc; p.dbg[4] = tl_acce; p.dbg[5] = tl_mapf; }
+#endif
   } else if (warp == 9) {
     // =========================== weight loader ================================================================
     int n = 0, g = 0;
@@ -304,13 +353,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
     // =========================== epilogue (warps 10-13; TMEM lane group = warp % 4) ============================
     const int lg = warp & 3;
     int n = 0;
+    TL_DECL;
+#ifdef SGB_SS_TIMELINE
+    long long tl_busy = 0;
+#endif
     for (int item = first; item < p.items; item += stride, n++) {
       const int ab = n & 1;
       const int tile = item / p.nparts, part = item % p.nparts;
       const int n0 = part * NT;
       const int nt = min(NT, p.N - n0);
       const int row = tile * T2_ROWS + lg * 32 + lane;
+      TL_BEGIN();
       mbar_wait(smem_u32(&bar_accf[ab]), (uint32_t)((n >> 1) & 1));
+      TL_END();
+#ifdef SGB_SS_TIMELINE
+      const long long te0 = clock64();
+#endif
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // a tile without any active pair (possible for the strided / inverse maps) never touched its accumulator: zero rows
       const uint32_t tbase = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * acc_cols);
@@ -409,7 +467,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) spconv_ss_kernel(Tc2Args p) {
           }
         }
       }
+#ifdef SGB_SS_TIMELINE
+      tl_busy += clock64() - te0;
+#endif
     }
+#ifdef SGB_SS_TIMELINE
+    if (tl_on && warp == 10) { p.dbg[7] = tl_acc; p.dbg[8] = tl_busy; }
+#endif
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -447,6 +511,7 @@ __global__ void act_pack_kernel(const float *__restrict__ x, int x_stride, int x
   yr[16] = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+static long long *g_ss_dbg = nullptr;  // only ever set by the SGB_SS_TIMELINE development build
 static int *g_oflow = nullptr;  // device flag shared by every launch of this process (per current device at first use)
 
 }  // namespace sgb
@@ -454,6 +519,10 @@ static int *g_oflow = nullptr;  // device flag shared by every launch of this pr
 using namespace sgb;
 
 extern "C" {
+
+#ifdef SGB_SS_TIMELINE
+void sgb_dev_ss_timeline(long long *d_buf) { g_ss_dbg = d_buf; }
+#endif
 
 int sgb_spconv_lo_shift(void) { return kLoShift2; }
 
@@ -520,6 +589,7 @@ int sgb_spconv_forward_ss(const float *d_in_pk, int in_stride, int Min, const in
   p.pk = (uint32_t *)d_pk_out; p.pk_stride = pk_stride; p.pk_coff = pk_coff;
   p.pk_scale = d_pk_scale; p.pk_shift = d_pk_shift; p.pk_relu = pk_relu; p.pk_fill = pk_fill;
   p.oflow = g_oflow;
+  p.dbg = g_ss_dbg;
   // Column parts: [B_hi | B_lo] is one operand of 2*NT <= 256 columns; few row tiles (deep levels) are cut further so the
   // work items cover the SMs. Every extra part re-gathers the tile's input rows, so stop at one item per SM.
   int sms = kNumSMs;

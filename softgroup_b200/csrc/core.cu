@@ -137,12 +137,4 @@ int sgb_device_available(void) {
   return n > 0 ? 1 : 0;
 }
 
-// Test hook: exclusive scan of int32 (used by tests/test_gpu_primitives.py).
-int sgb_test_exclusive_scan_i32(const int32_t *d_in, int32_t *d_out, long long n, int32_t *d_total, void *d_ws,
-                                size_t ws_bytes, void *stream) {
-  size_t need = sgb::scan_temp_elems((size_t)n) * sizeof(int32_t);
-  SGB_REQUIRE(ws_bytes >= need, SGB_ERR_WORKSPACE, "scan workspace too small");
-  return sgb::exclusive_scan_i32(d_in, d_out, (size_t)n, d_total, (int32_t *)d_ws, (cudaStream_t)stream);
-}
-size_t sgb_test_scan_workspace_bytes(long long n) { return sgb::scan_temp_elems((size_t)n) * sizeof(int32_t) + 256; }
 }

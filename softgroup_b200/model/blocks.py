@@ -151,7 +151,7 @@ class UBlock(nn.Module):
 
     def forward(self, input, next_act=None):
         deeper = len(self.nPlanes) > 1
-        fused = spconv.core.CONV_IMPL == 'ss' and input.features.is_cuda
+        fused = spconv.core.CONV_IMPL == 'tc' and input.features.is_cuda
         # consumer of the encoder blocks' output: the BatchNorm in front of the strided conv (deeper) or our caller's
         output = self.blocks(input, next_act=(self.conv[0] if deeper else next_act) if fused else None)
         if deeper:

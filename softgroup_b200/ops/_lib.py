@@ -52,15 +52,12 @@ SIGNATURES = {
     'sgb_spconv_forward': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, c_int, _P,
                                    _P, c_int, c_int, _P]),
     'sgb_spconv_tc_packed_floats': (c_longlong, [c_int, c_int, c_int]),
-    'sgb_spconv_forward_tc': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, c_int, _P,
-                                      _P, c_int, c_int, c_int, _P]),
-    'sgb_spconv_tc_lo_shift': (c_int, []),
-    'sgb_act_split': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     'sgb_spconv_lo_shift': (c_int, []),
     'sgb_spconv_overflow': (c_int, [_INTP, _P]),
+    'sgb_spconv_tc_plan': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, _INTP]),
     'sgb_act_pack': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    'sgb_spconv_forward_ss': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
-                                       c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    'sgb_spconv_forward_tc': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
+                                      c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'sgb_inst_count': (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P]),

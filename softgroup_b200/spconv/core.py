@@ -146,12 +146,12 @@ def build_down_map(indices, spatial_shape):
     return out_indices, mp, inv, [int(s) // 2 for s in spatial_shape]
 
 
-CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores (default), 'ffma' = CUDA-core fp32
+CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores (default), 'ffma' = CUDA-core fp32 (A/B only)
 
 
-def pack_weight_tc(W, lo_shift=None):
+def pack_weight_tc(W):
     """[K, Cin, Cout] f32 -> packed fp16 split for sgb_spconv_forward_tc (layout in sgb200.h):
-    [K, nkc, 4 chunks, 2 (hi, lo), N, 8 halves], hi = fp16(W), lo = fp16((W - hi) * 2^sgb_spconv_tc_lo_shift());
+    [K, nkc, 4 chunks, 2 (hi, lo), N, 8 halves], hi = fp16(W), lo = fp16((W - hi) * 2^sgb_spconv_lo_shift());
     returned as a float32-typed buffer."""
     K, Cin, Cout = W.shape
     N = (Cout + 15) // 16 * 16
@@ -160,33 +160,24 @@ def pack_weight_tc(W, lo_shift=None):
     Wp[:, :Cin, :Cout] = W
     Wp = Wp.view(K, nkc, 4, 8, N).permute(0, 1, 2, 4, 3).contiguous()  # [K, nkc, 4, N, 8]
     hi = Wp.half()
-    if lo_shift is None:
-        lo_shift = _lib.lib().sgb_spconv_tc_lo_shift()
-    lo = ((Wp - hi.float()) * float(2 ** lo_shift)).half()  # same scaling as the kernels
+    lo = ((Wp - hi.float()) * float(2 ** _lib.lib().sgb_spconv_lo_shift())).half()  # same scaling as the kernel
     packed = torch.stack([hi, lo], dim=3).contiguous()  # [K, nkc, 4, 2, N, 8] fp16
     return packed.view(torch.float32)
 
 
 class WeightPack(object):
-    """Weight of one conv in the kernels' formats: .kio [K,Cin,Cout] (CUDA-core kernel), .tc() the packed fp16 hi/lo
-    split of the round-1 tcgen05 kernel, .ss() the same split with the remainder scaled by 2^sgb_spconv_lo_shift() for
-    the round-2 kernel (spconv_ss.cu)."""
-    __slots__ = ('kio', 'packed', 'packed2')
+    """Weight of one conv in the kernels' formats: .kio [K,Cin,Cout] (CUDA-core kernel) and .tc(), the packed fp16
+    hi/lo split of the tcgen05 kernel."""
+    __slots__ = ('kio', 'packed')
 
     def __init__(self, kio):
         self.kio = kio
         self.packed = None
-        self.packed2 = None
 
     def tc(self):
         if self.packed is None:
             self.packed = pack_weight_tc(self.kio)
         return self.packed
-
-    def ss(self):
-        if self.packed2 is None:
-            self.packed2 = pack_weight_tc(self.kio, lo_shift=_lib.lib().sgb_spconv_lo_shift())
-        return self.packed2
 
 
 def act_pack(feats, in_stride, in_off, C, act=None, relu=None, out=None, out_coff=0, rows=None):
@@ -223,15 +214,15 @@ class Emit(object):
 
 def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, residual=None, bias=None, out=None,
                  out_stride=None, out_off=0, packed_in=None, emit=None, want_fp32=True, m_in=None):
-    """Thin wrapper over sgb_spconv_forward_ss / _tc / sgb_spconv_forward. W: WeightPack or [K, Cin, Cout] f32 tensor.
-    act: (scale, shift) or None. Round-2 kernel only: packed_in = the input already activated + packed (feats may then be
-    None, m_in = its row count); emit = Emit(...) makes the epilogue write the consumer's packed input; want_fp32 = False
-    skips the fp32 rows (single-consumer intermediates). Returns the fp32 tensor (or None); with emit, (fp32, packed)."""
+    """Thin wrapper over sgb_spconv_forward_tc (tcgen05) / sgb_spconv_forward (CUDA cores: SGB_CONV_IMPL=ffma, or shapes
+    outside the tensor path). W: WeightPack or [K, Cin, Cout] f32 tensor. act: (scale, shift) or None.
+    Tensor path: packed_in = the input already activated + packed (feats may then be None, m_in = its row count);
+    emit = Emit(...) makes the epilogue write the consumer's packed input; want_fp32 = False skips the fp32 rows
+    (single-consumer intermediates). Returns the fp32 tensor (or None); with emit, (fp32, packed)."""
     if not isinstance(W, WeightPack):
         W = WeightPack(W)
-    use_tc = CONV_IMPL in ('tc', 'ss') and Cout <= 256 and Cin <= 512
-    fused = use_tc and CONV_IMPL == 'ss'
-    assert fused or (packed_in is None and emit is None and want_fp32), 'packed I/O needs the round-2 conv kernel'
+    fused = CONV_IMPL == 'tc' and Cout <= 256 and Cin <= 512
+    assert fused or (packed_in is None and emit is None and want_fp32), 'packed I/O needs the tensor-core conv kernel'
     if out is None and want_fp32:
         out = torch.empty((Mout, Cout), dtype=torch.float32, device=(feats if feats is not None else packed_in).device)
         out_stride = Cout
@@ -243,9 +234,8 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
     nbytes = 4 * m_in * Cin + 4 * K * Cin * Cout + (4 * K * Mout if mp is not None else 0) + 4 * Mout * Cout
     if residual is not None:
         nbytes += 4 * Mout * Cout
-    name = ('spconv_tc_kernel' if use_tc else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
+    name = ('spconv_tc_kernel' if fused else 'spconv_kernel') + ('' if mp is not None else '(1x1/linear)')
     if fused:
-        name = 'spconv_ss_kernel' + ('' if mp is not None else '(1x1/linear)')
         pk = packed_in if packed_in is not None else act_pack(feats, in_stride, in_off, Cin, act=act, relu=act is not None)
         pk_out, pk_stride, pk_coff, es, eh, fill = None, 0, 0, None, None, 0
         if emit is not None:
@@ -254,40 +244,16 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
             pk_out, pk_stride, pk_coff, es, eh, fill = emit.buf, emit.buf.size(1), emit.coff, emit.scale, emit.shift, int(emit.fill)
         with profiler.record(name, nbytes):
             check(
-                _lib.lib().sgb_spconv_forward_ss(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.ss()), Cin, Cout,
+                _lib.lib().sgb_spconv_forward_tc(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.tc()), Cin, Cout,
                                                  ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride or 0, out_off,
                                                  ptr(pk_out), pk_stride, pk_coff, ptr(es), ptr(eh), 1, fill, _stream()),
-                'sgb_spconv_forward_ss')
+                'sgb_spconv_forward_tc')
         return (out, pk_out) if emit is not None else out
-    if use_tc:
-        # activation (+ split into fp16 hi/lo) once per tensor instead of once per gathered (row, offset) in the conv
-        K_eff = K
-        packed_in = None
-        if K_eff > 1 or act is not None:
-            cpad = (Cin + 31) // 32 * 32
-            packed_in = torch.empty((m_in, cpad), dtype=torch.float32, device=feats.device)
-            with profiler.record('act_split', 8 * m_in * Cin):
-                check(
-                    _lib.lib().sgb_act_split(ptr(feats), in_stride, in_off, ptr(scale), ptr(shift), 1, ptr(packed_in), m_in,
-                                             Cin, _stream()), 'sgb_act_split')
     with profiler.record(name, nbytes):
-        if use_tc:
-            if packed_in is not None:
-                check(
-                    _lib.lib().sgb_spconv_forward_tc(ptr(packed_in), packed_in.size(1), 0, ptr(mp), K, Mout, ptr(W.tc()),
-                                                     Cin, Cout, None, None, ptr(residual), rs, ro, ptr(bias), ptr(out),
-                                                     out_stride, out_off, 1, _stream()), 'sgb_spconv_forward_tc')
-            else:
-                check(
-                    _lib.lib().sgb_spconv_forward_tc(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.tc()), Cin,
-                                                     Cout, ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias),
-                                                     ptr(out), out_stride, out_off, 0, _stream()),
-                    'sgb_spconv_forward_tc')
-        else:
-            check(
-                _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.kio), Cin, Cout,
-                                              ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
-                                              out_stride, out_off, _stream()), 'sgb_spconv_forward')
+        check(
+            _lib.lib().sgb_spconv_forward(ptr(feats), in_stride, in_off, ptr(mp), K, Mout, ptr(W.kio), Cin, Cout,
+                                          ptr(scale), ptr(shift), ptr(residual), rs, ro, ptr(bias), ptr(out),
+                                          out_stride, out_off, _stream()), 'sgb_spconv_forward')
     return out
 
 
@@ -406,16 +372,17 @@ class SparseInverseConv3d(_SparseConvBase):
     def __init__(self, in_channels, out_channels, kernel_size, indice_key=None, bias=True):
         super().__init__(in_channels, out_channels, kernel_size, bias=bias, indice_key=indice_key)
 
-    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0):
-        f = self._features(x)
+    def forward(self, x, act=None, residual=None, out=None, out_stride=None, out_off=0, **fuse):
+        f = self._features(x, fuse)
         rb = x.find_indice_pair(self.indice_key)
         assert rb is not None and rb['kind'] == 'down', 'SparseInverseConv3d needs the pairs of indice_key %r' % (
             self.indice_key, )
         M = rb['in_indices'].size(0)
-        o = conv_forward(f, f.stride(0), 0, rb['inv_map'], 8, M, self.weight_kio(), self.in_channels,
+        o = conv_forward(f, _stride0(f), 0, rb['inv_map'], 8, M, self.weight_kio(), self.in_channels,
                          self.out_channels, act=act, residual=residual, bias=self.bias, out=out,
-                         out_stride=out_stride, out_off=out_off)
-        return SparseConvTensor(o, rb['in_indices'], rb['in_shape'], x.batch_size, x.grid, x.indice_dict)
+                         out_stride=out_stride, out_off=out_off, m_in=x.indices.size(0), **fuse)
+        t = SparseConvTensor(None, rb['in_indices'], rb['in_shape'], x.batch_size, x.grid, x.indice_dict)
+        return _wrap(t, o, fuse)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -459,7 +426,7 @@ class SparseSequential(SparseModule):
     def forward(self, input, residual=None, out=None, out_stride=None, out_off=0, next_act=None, emit_buf=None):
         """residual / out* apply to the LAST sparse conv of the sequence (fused epilogue).
 
-        Round-2 kernel (CONV_IMPL == 'ss'): activations travel PACKED between convolutions. A conv followed inside this
+        Tensor-core path: activations travel PACKED between convolutions. A conv followed inside this
         sequence by BatchNorm+ReLU+conv writes only the packed rows its successor reads (that BatchNorm+ReLU folded into
         its epilogue, no fp32 rows at all); `next_act` = the BatchNorm module that will consume this sequence's OUTPUT
         (behind a ReLU, in front of a conv) makes the last conv emit those packed rows next to its fp32 rows, into
@@ -468,7 +435,7 @@ class SparseSequential(SparseModule):
         mods = list(self._modules.values())
         conv_idx = [i for i, m in enumerate(mods) if isinstance(m, _SparseConvBase)]
         last_conv = conv_idx[-1] if conv_idx else -1
-        fused = CONV_IMPL == 'ss'
+        fused = CONV_IMPL == 'tc'
         pending = None  # (scale, shift, relu, bn module)
         carry = None    # packed input prepared by the previous conv of this sequence for exactly `pending`
         x = input

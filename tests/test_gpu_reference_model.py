@@ -38,6 +38,20 @@ def ref_module():
     return m
 
 
+class _Cfg(dict):
+    """Attribute access on nested config dicts (the reference reads `self.test_cfg.x4_split`, `self.grouping_cfg.radius`:
+    tools/test.py builds its configs with Munch)."""
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    @classmethod
+    def wrap(cls, d):
+        return cls({k: (cls.wrap(v) if isinstance(v, dict) else v) for k, v in d.items()})
+
+
 def _pair(ref_module, cfg, calibrated=None, scan=None):
     ours = SoftGroup(**cfg).eval()
     fill_seeded(ours, WEIGHT_SEED)
@@ -46,7 +60,7 @@ def _pair(ref_module, cfg, calibrated=None, scan=None):
     ours = ours.cuda()
     if calibrated is None:
         harness.calibrate_heads(ours, harness.to_host_batch(scan))
-    ref = ref_module.SoftGroup(**cfg)
+    ref = ref_module.SoftGroup(**_Cfg.wrap(cfg))
     ref.eval()  # the reference overrides train() without returning self (softgroup.py:98-104): no chaining
     ref.load_state_dict(ours.state_dict(), strict=True)  # identical names and shapes: checkpoints load unchanged
     return ours, ref.cuda()
