@@ -24,10 +24,13 @@
 
 namespace sgb {
 
-constexpr int kBqThreads = 1024;
+// Two 512-thread CTAs per SM (round 2; round 1 ran one 1024-thread CTA with a 160 KB staging area): the CTA-wide
+// barriers of the staging / ordering phases were 39 % of the stall samples (profiles/r1_ncu_bq_summary.txt) -- with two
+// CTAs one stages while the other queries, and each barrier spans half as many warps.
+constexpr int kBqThreads = 512;
 constexpr int kBqWarps = kBqThreads / 32;
-constexpr int kBqSMax = 10240;  // staged candidates per cell (16 B each, 160 KB)
-constexpr int kBmWords = 8192;  // index bitmap for the linear-time ordering of a stencil (32 KB + 16 KB prefix)
+constexpr int kBqSMax = 5120;   // staged candidates per work item (16 B each, 80 KB); larger stencils take the exact scan path
+constexpr int kBmWords = 4096;  // index bitmap for the linear-time ordering of a stencil (16 KB + 8 KB prefix)
 constexpr int kCellBias = 131072;
 constexpr int kMaxSeg = 1023;
 
@@ -170,7 +173,7 @@ __device__ __forceinline__ void bq_emit(int qi, int cnt, const int32_t *stage, i
   for (int k = lane; k < cw; k += 32) idx[(size_t)base + k] = stage[k];
 }
 
-__global__ void __launch_bounds__(kBqThreads) bq_query_kernel(const float *__restrict__ xyz,
+__global__ void __launch_bounds__(kBqThreads, 2) bq_query_kernel(const float *__restrict__ xyz,
                                                               const int32_t *__restrict__ batch_idxs,
                                                               const int32_t *__restrict__ batch_offsets, int n,
                                                               float radius, long long capacity,
@@ -426,7 +429,7 @@ static int bq_launch(int n, long long capacity, float radius, const float *xyz, 
     SGB_CUDA_CHECK(cudaFuncSetAttribute(bq_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  int grid = std::min(std::max(n, 1), kNumSMs);
+  int grid = std::min(std::max(n, 1), 2 * kNumSMs);
   bq_query_kernel<<<grid, kBqThreads, smem, st>>>(xyz, batch_idxs, batch_offsets, n, radius, capacity, idx, start_len, w);
   SGB_LAUNCH_CHECK();
   return SGB_OK;

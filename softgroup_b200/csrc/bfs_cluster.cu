@@ -106,9 +106,20 @@ __global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, 
     if (lu >= prev) continue;  // warp-uniform: nothing new to tell the out-neighbours
     pushed_any = true;
     int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
-    for (int j = lane; j < l; j += 32) {
-      int v = __ldg(&idxs[(size_t)s + j]);
-      if (ld_ca_i32(&w.label[v]) > lu) atomicMin(&w.label[v], lu);  // a stale (higher) value only costs a redundant atomic
+    // four independent (index, label) load pairs in flight per lane: the loop is latency bound (a list entry, then the
+    // label it points to), not bandwidth bound
+    for (int j0 = 0; j0 < l; j0 += 128) {
+      int v[4], lv[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int j = j0 + t * 32 + lane;
+        v[t] = (j < l) ? __ldg(&idxs[(size_t)s + j]) : -1;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) lv[t] = (v[t] >= 0) ? ld_ca_i32(&w.label[v[t]]) : 0;
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        if (v[t] >= 0 && lv[t] > lu) atomicMin(&w.label[v[t]], lu);  // a stale (higher) value only costs a redundant atomic
     }
     __syncwarp();
     if (lane == 0) w.wins[u] = lu;
@@ -522,7 +533,22 @@ int sgb_bfs_cluster_fill(const int32_t *d_ball_query_idxs, const int32_t *d_star
     SGB_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, (size_t)nCluster * 4, st));
     bfs_members_kernel<<<nb, 256, 0, st>>>(N, d_cluster_offsets, w);
     SGB_LAUNCH_CHECK();
-    int n_cl = std::min(nCluster, kNumSMs / kCl);
+    // as many 8-CTA clusters as the device keeps resident at once (several CTAs per SM: the kernel is latency bound on its
+    // per-level cluster barriers, so components in flight -- not threads per component -- is what fills the machine)
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kNumSMs * 4 / kCl * kCl);
+      cfg.blockDim = dim3(kClThreads);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, bfs_emit2_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = kNumSMs / kCl; }
+      max_clusters = n;
+    }
+    int n_cl = std::min(nCluster, max_clusters);
     bfs_emit2_kernel<<<n_cl * kCl, kClThreads, 0, st>>>(d_ball_query_idxs, d_start_len, d_cluster_offsets, d_cluster_idxs,
                                                        nCluster, W, (uint32_t *)d_scratch, w);
     SGB_LAUNCH_CHECK();

@@ -87,6 +87,8 @@ class Custom1x1Subm3d(spconv.SparseConv3d):
         out_tensor.grid = input.grid
         return out_tensor
 
+    forward._sgb_fused = True
+
 
 class ResidualBlock(SparseModule):
 

@@ -385,6 +385,16 @@ class SparseInverseConv3d(_SparseConvBase):
         return _wrap(t, o, fuse)
 
 
+# forwards that understand act= / residual= / out= / packed_in= / emit= ...: a subclass that overrides forward with the
+# plain spconv signature `forward(self, input)` (the reference's Custom1x1Subm3d, blocks.py:31-41) is an opaque module
+for _cls in (SubMConv3d, SparseConv3d, SparseInverseConv3d):
+    _cls.forward._sgb_fused = True
+
+
+def _takes_fusion(m):
+    return isinstance(m, _SparseConvBase) and getattr(type(m).forward, '_sgb_fused', False)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # SparseSequential with BN/ReLU -> conv peephole fusion
 # ---------------------------------------------------------------------------------------------------------
@@ -433,7 +443,7 @@ class SparseSequential(SparseModule):
         `emit_buf` = (packed buffer, channel offset, scale, shift) when the consumer reads a concat buffer. Child
         modules that take the same hint (ResidualBlock) are chained the same way."""
         mods = list(self._modules.values())
-        conv_idx = [i for i, m in enumerate(mods) if isinstance(m, _SparseConvBase)]
+        conv_idx = [i for i, m in enumerate(mods) if _takes_fusion(m)]
         last_conv = conv_idx[-1] if conv_idx else -1
         fused = CONV_IMPL == 'tc'
         pending = None  # (scale, shift, relu, bn module)
@@ -452,7 +462,7 @@ class SparseSequential(SparseModule):
             if isinstance(m, nn.ReLU) and pending is not None and not pending[2]:
                 pending = (pending[0], pending[1], True, pending[3])
                 continue
-            if isinstance(m, _SparseConvBase):
+            if _takes_fusion(m):
                 act, fuse = None, {}
                 if pending is not None:
                     if pending[2]:
@@ -468,7 +478,7 @@ class SparseSequential(SparseModule):
                 if fused and is_sparse_in and m.out_channels <= 256 and m.in_channels <= 512:
                     nxt = mods[i + 1:i + 4]
                     if (len(nxt) == 3 and isinstance(nxt[0], nn.BatchNorm1d) and not nxt[0].training and
-                            isinstance(nxt[1], nn.ReLU) and isinstance(nxt[2], _SparseConvBase) and i != last_conv):
+                            isinstance(nxt[1], nn.ReLU) and _takes_fusion(nxt[2]) and i != last_conv):
                         es, eb = fold_bn(nxt[0])
                         fuse['emit'] = Emit(es, eb, nxt[0])
                         fuse['want_fp32'] = False  # the intermediate never leaves this sequence
