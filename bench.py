@@ -472,9 +472,12 @@ def main():
         dev_ms, dev_wall, out = timed(step_device, args.steps, max(args.warmup, 3))
         launches = (_lib.lib().sgb_launch_count() - l0)
         e2e_ms, e2e_wall, ret = timed(lambda: harness.run_scan(model, hb, inject_pointwise=inj), args.steps, 2)
-        # instrumented pass (per-op CUDA events) -> dominant kernel and its roofline
+        # instrumented pass (per-op CUDA events) -> dominant kernel and its roofline. It runs the module path (one ctypes call
+        # per launch, same kernels and arguments as the compiled plan of the timed legs) so that every launch has its own event
         profiler.reset()
+        model.use_plan = False
         timed(step_device, min(args.steps, 5), 1, instrument=True)
+        model.use_plan = True
     # launches counted over warmup+steps of the first leg -> per timed region
     launches_per_step = launches // (args.steps + max(args.warmup, 3))
 

@@ -27,10 +27,14 @@ namespace sgb {
 // Two 512-thread CTAs per SM (round 2; round 1 ran one 1024-thread CTA with a 160 KB staging area): the CTA-wide
 // barriers of the staging / ordering phases were 39 % of the stall samples (profiles/r1_ncu_bq_summary.txt) -- with two
 // CTAs one stages while the other queries, and each barrier spans half as many warps.
-constexpr int kBqThreads = 512;
-constexpr int kBqWarps = kBqThreads / 32;
-constexpr int kBqSMax = 5120;   // staged candidates per work item (16 B each, 80 KB); larger stencils take the exact scan path
-constexpr int kBmWords = 4096;  // index bitmap for the linear-time ordering of a stencil (16 KB + 8 KB prefix)
+// Pass 0 of the query: 512-thread CTAs, two per SM, 5120 staged candidates (80 KB) each. Work items whose stencil is
+// larger (the core cells of collapsed objects: several thousand candidates) are only NOTED in pass 0 and processed by
+// pass 1: one 1024-thread CTA per SM with a 10240-candidate staging area (the round-1 configuration). Measured (GPU
+// calls 6/7 of round 2): the small configuration alone is 1.7x faster on fragmented predictions (2.34 -> 1.37 ms) but
+// 1.4x slower on the clean 40-object scan (1.35 -> 1.89 ms, its cores overflow into the exact-scan path).
+template <int PASS> struct BqCfg;
+template <> struct BqCfg<0> { static constexpr int kThreads = 512, kSMax = 5120, kBmWords = 4096, kPerSM = 2; };
+template <> struct BqCfg<1> { static constexpr int kThreads = 1024, kSMax = 10240, kBmWords = 8192, kPerSM = 1; };
 constexpr int kCellBias = 131072;
 constexpr int kMaxSeg = 1023;
 
@@ -45,7 +49,8 @@ struct BqWs {
   float4 *sorted;            // [n] (x,y,z,idx)
   int32_t *chunk_cell;       // [2n] work item -> cell id
   int32_t *chunk_q0;         // [2n] work item -> first query of the cell handled by this item
-  int32_t *scalars;          // 0: ncells, 1: work counter, 2: error flag, 3: total
+  int32_t *big_items;        // [2n] work items pass 0 left to pass 1 (count in scalars[5])
+  int32_t *scalars;          // 0: ncells, 1: work counter, 2: error flag, 3: total, 4: items, 5: big items, 6: pass-1 counter
   int32_t *scan_tmp;
   uint32_t cap;
 };
@@ -66,6 +71,7 @@ static bool bq_carve(void *ws, size_t bytes, int n, BqWs &w) {
   w.sorted = a.take<float4>((size_t)n + 1);
   w.chunk_cell = a.take<int32_t>(2 * (size_t)n + 2);
   w.chunk_q0 = a.take<int32_t>(2 * (size_t)n + 2);
+  w.big_items = a.take<int32_t>(2 * (size_t)n + 2);
   w.scan_tmp = a.take<int32_t>(scan_temp_elems((size_t)n + 1));
   return w.scan_tmp != nullptr;
 }
@@ -173,12 +179,15 @@ __device__ __forceinline__ void bq_emit(int qi, int cnt, const int32_t *stage, i
   for (int k = lane; k < cw; k += 32) idx[(size_t)base + k] = stage[k];
 }
 
-__global__ void __launch_bounds__(kBqThreads, 2) bq_query_kernel(const float *__restrict__ xyz,
+template <int PASS>
+__global__ void __launch_bounds__(BqCfg<PASS>::kThreads, BqCfg<PASS>::kPerSM) bq_query_kernel(const float *__restrict__ xyz,
                                                               const int32_t *__restrict__ batch_idxs,
                                                               const int32_t *__restrict__ batch_offsets, int n,
                                                               float radius, long long capacity,
                                                               int32_t *__restrict__ idx,
                                                               int32_t *__restrict__ start_len, BqWs w) {
+  constexpr int kBqThreads = BqCfg<PASS>::kThreads, kBqWarps = kBqThreads / 32, kBqSMax = BqCfg<PASS>::kSMax;
+  constexpr int kBmWords = BqCfg<PASS>::kBmWords;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *S = reinterpret_cast<float4 *>(smem_raw);  // [kBqSMax]
   uint32_t *bm = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * kBqSMax);                      // [kBmWords]
@@ -189,14 +198,15 @@ __global__ void __launch_bounds__(kBqThreads, 2) bq_query_kernel(const float *__
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float r2 = __fmul_rn(radius, radius);
-  const int nitems = w.scalars[4];
+  // pass 0 walks all work items; pass 1 the items pass 0 noted as too large for its staging area
+  const int nitems = (PASS == 0) ? w.scalars[4] : w.scalars[5];
 
   while (true) {
     __syncthreads();
-    if (tid == 0) s_cell = atomicAdd(&w.scalars[1], 1);
+    if (tid == 0) s_cell = atomicAdd(&w.scalars[PASS == 0 ? 1 : 6], 1);
     __syncthreads();
-    const int item = s_cell;
-    if (item >= nitems) break;
+    if (s_cell >= nitems) break;
+    const int item = (PASS == 0) ? s_cell : w.big_items[s_cell];
     const int cell = w.chunk_cell[item];
     const int cslot = w.cell_slot[cell];
     const unsigned long long ckey = w.keys[cslot];
@@ -225,6 +235,10 @@ __global__ void __launch_bounds__(kBqThreads, 2) bq_query_kernel(const float *__
     const int total_s = nb_off[27];
     const int q_first = w.chunk_q0[item];
     const int q_start = w.slot_start[cslot] + q_first, q_cnt = min(kBqChunk, w.slot_cnt[cslot] - q_first);
+    if (PASS == 0 && total_s > kBqSMax) {  // too large for this configuration's staging area: left to pass 1
+      if (tid == 0) w.big_items[atomicAdd(&w.scalars[5], 1)] = item;
+      continue;
+    }
 
     if (total_s <= kBqSMax) {
       // ---- order the stencil by point index. Point indices are distinct, so the sorted position of a record is
@@ -423,14 +437,20 @@ static int bq_launch(int n, long long capacity, float radius, const float *xyz, 
   SGB_LAUNCH_CHECK();
   bq_scatter_kernel<<<nb, 256, 0, st>>>(xyz, n, w);
   SGB_LAUNCH_CHECK();
-  size_t smem = sizeof(float4) * kBqSMax + 4 * kBmWords + 2 * kBmWords;
+  constexpr size_t smem0 = sizeof(float4) * BqCfg<0>::kSMax + 6 * BqCfg<0>::kBmWords;
+  constexpr size_t smem1 = sizeof(float4) * BqCfg<1>::kSMax + 6 * BqCfg<1>::kBmWords;
   static bool attr_set = false;
   if (!attr_set) {
-    SGB_CUDA_CHECK(cudaFuncSetAttribute(bq_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(bq_query_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    SGB_CUDA_CHECK(cudaFuncSetAttribute(bq_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     attr_set = true;
   }
-  int grid = std::min(std::max(n, 1), 2 * kNumSMs);
-  bq_query_kernel<<<grid, kBqThreads, smem, st>>>(xyz, batch_idxs, batch_offsets, n, radius, capacity, idx, start_len, w);
+  bq_query_kernel<0><<<std::min(std::max(n, 1), BqCfg<0>::kPerSM * kNumSMs), BqCfg<0>::kThreads, smem0, st>>>(
+      xyz, batch_idxs, batch_offsets, n, radius, capacity, idx, start_len, w);
+  SGB_LAUNCH_CHECK();
+  // the items pass 0 noted (stencils of 5121..10240 candidates stay on the staged path; beyond that the exact scan)
+  bq_query_kernel<1><<<std::min(std::max(n, 1), kNumSMs), BqCfg<1>::kThreads, smem1, st>>>(xyz, batch_idxs, batch_offsets, n, radius,
+                                                                                         capacity, idx, start_len, w);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
@@ -445,7 +465,7 @@ size_t sgb_ballquery_workspace_bytes(int n) {
   if (n < 0) n = 0;
   size_t cap = bq_cap(n);
   size_t b = align_up(64 * 4) + align_up(cap * 8) + 3 * align_up(cap * 4) + 3 * align_up(((size_t)n + 1) * 4) +
-             2 * align_up((2 * (size_t)n + 2) * 4) +
+             3 * align_up((2 * (size_t)n + 2) * 4) +
              align_up(((size_t)n + 1) * 16) + align_up(scan_temp_elems((size_t)n + 1) * 4);
   return b + 1024;
 }

@@ -147,6 +147,10 @@ class SoftGroup(nn.Module):
             mod = getattr(self, mod)
             for param in mod.parameters():
                 param.requires_grad = False
+        # the backbone and the tiny U-Net run as compiled launch plans through ONE C call each (model/unet_plan.py); False =
+        # the module path, one ctypes call per launch (same kernels, same results; used for per-kernel instrumentation)
+        self.use_plan = True
+        self._plans = {}
         self.stage_ms = None  # filled when profile_stages is set
         self.profile_stages = False
 
@@ -292,6 +296,27 @@ class SoftGroup(nn.Module):
         return dict(c) if isinstance(c, dict) else {k: getattr(c, k) for k in ('scale', 'spatial_shape') if hasattr(c, k)}
 
     # ------------------------------------------------------------------------------------------------------
+    def _run_stack(self, name, input_conv, unet, output_layer, x):
+        """input_conv -> unet -> output_layer on SparseConvTensor x -> fp32 feature rows. Compiled plan (one C call) when
+        use_plan is set and the tensor path applies, else the module path."""
+        from ..spconv import core
+        if (self.use_plan and core.CONV_IMPL == 'tc' and x.features.is_cuda and not self.training and
+                max(unet.nPlanes) <= 256):
+            ver = sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+            hit = self._plans.get(name)
+            if hit is None or hit[0] != ver:
+                from .unet_plan import compile_backbone
+                hit = (ver, compile_backbone(input_conv, unet, output_layer))
+                self._plans[name] = hit
+            return hit[1].run(x)
+        out = x
+        if input_conv is not None:
+            out = input_conv(out)
+        out = unet(out)
+        if output_layer is not None:
+            out = output_layer(out)
+        return out.features
+
     def forward_backbone(self, input, input_map, x4_split=False, lvl_fusion=False):
         """softgroup.py:363-378."""
         if x4_split:
@@ -299,16 +324,14 @@ class SoftGroup(nn.Module):
             output_feats = self.forward_4_parts(input, input_map)
             output_feats = self.merge_4_parts(output_feats)
         elif lvl_fusion:
-            output = self.output_layer(self.unet(self.input_conv(input)))
-            output_feats = output.features  # stays on voxel rows (softgroup.py:373-374)
+            output_feats = self._run_stack('backbone', self.input_conv, self.unet, self.output_layer, input)  # voxel rows (:373-374)
         else:
             from ..ops import _lib
             from ..ops._lib import check, ptr
             import ctypes
-            output = self.input_conv(input)
-            output = self.unet(output)
-            output = self.output_layer(output)
-            vf = output.features
+            vf = self._run_stack('backbone', self.input_conv, self.unet, self.output_layer, input)
+            if vf.stride(0) != vf.size(1):
+                vf = vf.contiguous()
             N = input_map.size(0)
             output_feats = torch.empty((N, vf.size(1)), dtype=vf.dtype, device=vf.device)
             # output_feats[input_map.long()] (:374) -- the "devoxelize" gather
@@ -331,10 +354,7 @@ class SoftGroup(nn.Module):
             coords[:, 0] = 0
             x_new = spconv.SparseConvTensor(indices=coords, features=feats, spatial_shape=x.spatial_shape,
                                             batch_size=1)
-            out = self.input_conv(x_new)
-            out = self.unet(out)
-            out = self.output_layer(out)
-            outs.append(out.features)
+            outs.append(self._run_stack('backbone', self.input_conv, self.unet, self.output_layer, x_new))
         outs = torch.cat(outs, dim=0)
         return outs[input_map.long()]
 
@@ -548,8 +568,8 @@ class SoftGroup(nn.Module):
 
     def forward_instance(self, inst_feats, inst_map):
         """softgroup.py:509-522."""
-        feats = self.tiny_unet(inst_feats)
-        feats = self.tiny_unet_outputlayer(feats)
+        f = self._run_stack('tiny', None, self.tiny_unet, self.tiny_unet_outputlayer, inst_feats)
+        feats = inst_feats.replace_feature(f)
         mask_scores = self.mask_linear(feats.features)
         mask_scores = mask_scores[inst_map.long()]
         instance_batch_idxs = feats.indices[:, 0][inst_map.long()]

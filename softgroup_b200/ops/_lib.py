@@ -58,6 +58,7 @@ SIGNATURES = {
     'sgb_act_pack': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     'sgb_spconv_forward_tc': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
                                       c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    'sgb_unet_run': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'sgb_inst_count': (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P]),

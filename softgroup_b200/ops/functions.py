@@ -196,6 +196,13 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     return cluster_idxs, cluster_offsets
 
 
+# The reference's wrapper returns the clusters on the device of its inputs -- the CPU, it copies the lists there first
+# (softgroup.py:458) -- and later indexes that CPU tensor with a CUDA mask (softgroup.py:570), which PyTorch >= 2 rejects.
+# install_as_reference_backends(keep_clusters_on_gpu=True) sets this switch so that the UNMODIFIED reference model runs on
+# a current PyTorch: clusters then stay on the GPU (where they were computed) whatever device the inputs came from.
+KEEP_CLUSTERS_ON_GPU = False
+
+
 class BFSCluster(Function):
     """functions.py:278-308. threshold semantics of bfs_cluster.cpp:70-82."""
 
@@ -214,7 +221,7 @@ class BFSCluster(Function):
         if idxs.numel() == 0:
             idxs = torch.zeros(1, dtype=torch.int32, device=sl.device)
         cidx, coff = bfs_cluster_segments(idxs, sl, thr)
-        if on_cpu:
+        if on_cpu and not KEEP_CLUSTERS_ON_GPU:
             cidx, coff = cidx.cpu(), coff.cpu()
         return cidx, coff
 

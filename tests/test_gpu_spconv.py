@@ -203,3 +203,36 @@ def test_backbone_vs_oracle(channels, num_blocks):
     assert out.shape == want.shape
     assert _rel(out, want) < 1e-4  # north star: float features within 1e-4 relative
     np.testing.assert_allclose(out, want, rtol=1e-3, atol=1e-4 * np.abs(want).max())
+
+
+@pytest.mark.parametrize('channels,num_blocks,n', [(16, 4, 6000), (32, 7, 30000)])
+def test_plan_equals_module_path(channels, num_blocks, n):
+    """The compiled launch plan (model/unet_plan.py -> ONE sgb_unet_run call) issues the same kernels with the same
+    arguments as the module path (one ctypes call per launch): bit-identical features, for the backbone (input conv +
+    U-Net + output layer) and for the tiny U-Net of the instance branch (no input conv)."""
+    import oracle
+    torch.manual_seed(0)
+    scan = synth.make_scan('c2_scannet', seed=1, n_points=n)
+    vc, v2p, p2v = oracle.voxelization_idx(scan['coords'], 1, 4)
+    feats = np.concatenate([scan['feats'], scan['coords_float']], 1).astype(np.float32)
+    vfeats = oracle.voxelization(feats, p2v, 4)
+    model = SoftGroup(**model_cfg('scannet', channels=channels, num_blocks=num_blocks)).cuda().eval()
+    _randomize_bn(model, 2)
+
+    def run(use_plan, name, ic, un, ol, f, idx, shape, bs):
+        model.use_plan = use_plan
+        x = spconv.SparseConvTensor(f, idx, shape, bs)
+        with torch.no_grad():
+            return model._run_stack(name, ic, un, ol, x).clone()
+
+    f, idx = _cuda(vfeats), _cuda(vc.astype(np.int32))
+    a = run(True, 'backbone', model.input_conv, model.unet, model.output_layer, f, idx, scan['spatial_shape'], 1)
+    b = run(False, 'backbone', model.input_conv, model.unet, model.output_layer, f, idx, scan['spatial_shape'], 1)
+    assert a.shape == b.shape and torch.equal(a, b)
+    # tiny U-Net on a 20^3 grid per "proposal" (clusters_voxelization output shape)
+    rng = np.random.RandomState(3)
+    occ = np.argwhere(rng.rand(5, 20, 20, 20) < 0.08).astype(np.int32)
+    tf = torch.from_numpy(rng.randn(len(occ), channels).astype(np.float32)).cuda()
+    a = run(True, 'tiny', None, model.tiny_unet, model.tiny_unet_outputlayer, tf, _cuda(occ), [20, 20, 20], 5)
+    b = run(False, 'tiny', None, model.tiny_unet, model.tiny_unet_outputlayer, tf, _cuda(occ), [20, 20, 20], 5)
+    assert torch.equal(a, b)
