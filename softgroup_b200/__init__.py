@@ -9,7 +9,7 @@ import sys
 __version__ = '0.1.0'
 
 
-def install_as_reference_backends(keep_clusters_on_gpu=False):
+def install_as_reference_backends(torch2_compat=False):
     """Register this package's modules under the names the UNMODIFIED reference imports, so that
     `softgroup/model/*.py` and `tools/test.py` of thangvubk/SoftGroup run on these kernels:
         import spconv.pytorch as spconv          -> softgroup_b200.spconv.pytorch
@@ -17,11 +17,12 @@ def install_as_reference_backends(keep_clusters_on_gpu=False):
         from . import ops  (softgroup/ops/functions.py:4, the compiled extension) is bypassed by providing
         `softgroup.ops` = softgroup_b200.ops
     Call before importing `softgroup`. See INTEGRATION.md.
-    keep_clusters_on_gpu: `bfs_cluster` returns CUDA tensors even for the CPU inputs the reference hands it -- needed to
-    run the unmodified reference on PyTorch >= 2, which no longer lets softgroup.py:570 index a CPU tensor with a CUDA mask."""
+    torch2_compat: the reference indexes the CPU cluster tensor with a CUDA mask (softgroup.py:570), which PyTorch >= 2
+    rejects; with this switch `bfs_cluster` returns its CPU result as a tensor subclass that copies CUDA indices to the host
+    first (ops/functions.py:HostIndexTensor), so the unmodified reference model runs on a current PyTorch."""
     from . import ops
     from .ops import functions as _f
-    _f.KEEP_CLUSTERS_ON_GPU = bool(keep_clusters_on_gpu)
+    _f.TORCH2_COMPAT = bool(torch2_compat)
     from . import spconv as sp
     from .spconv import pytorch as sp_pt
     sys.modules.setdefault('spconv', sp)

@@ -11,9 +11,12 @@ softgroup.py:65) and emits one `sgb_unet_op` record per launch with the SAME fus
     of the concat buffer, the inverse conv into the right half (fp32 and packed twins);
   * the 1x1 skip of the first tail block reads the raw concat buffer (one pack pass).
 
-Per scan `Plan.run` builds the rulebooks of every level (the only host synchronisations: the six parent counts), carves
-ONE arena for all intermediate buffers and makes ONE `sgb_unet_run` call. The launches are the same kernels with the same
-arguments as the module path, so the result is bit-identical to it (tests/test_gpu_spconv.py::test_plan_equals_module_path).
+Per scan `Plan.run` walks the plan in SEGMENTS, one `sgb_unet_run` call each (7 + 1 for the seven-level backbone): a
+segment ends where the next launch needs a U-Net level whose rulebook does not exist yet. Opening a level costs one host
+wait (the parent count of the strided rulebook); it is taken right after the previous segment's convolutions were enqueued,
+so the GPU keeps working through it. One arena per level holds that level's intermediate buffers. The launches are the
+same kernels with the same arguments as the module path, so the result is bit-identical to it
+(tests/test_gpu_spconv.py::test_plan_equals_module_path).
 """
 import ctypes
 
@@ -22,7 +25,7 @@ from torch import nn
 
 from .. import profiler
 from ..ops import _lib
-from ..ops._lib import check, ptr
+from ..ops._lib import check
 from ..spconv import core
 from ..spconv.core import fold_bn
 
@@ -128,6 +131,18 @@ class Plan(object):
             for k, v in d.items():
                 setattr(arr[i], k, v)
         self._c_ops = arr
+        # segments of consecutive ops that need no level beyond the ones already opened: (first op, last op + 1, levels that
+        # must be open before it runs). Opening level k = strided rulebook of level k-1 (a host wait for the parent count)
+        # + submanifold rulebook of level k. The wait happens while the previous segment's convolutions are still running.
+        self.segments = []
+        opened, start = 0, 0
+        for i, d in enumerate(self.ops):
+            need = max(d['level_in'], d['level_out'])
+            if need > opened:
+                if i > start:
+                    self.segments.append((start, i, opened))
+                start, opened = i, need
+        self.segments.append((start, len(self.ops), opened))
 
     def run(self, x):
         """x: SparseConvTensor (fp32 features [M0, Cin]) -> fp32 features [M0, Cout] of the compiled stack."""
@@ -135,49 +150,68 @@ class Plan(object):
         feats = x.features.contiguous()
         dev = feats.device
         L = self.n_levels
-        # rulebooks of every level (cached in the tensor's indice_dict exactly like the module path does)
-        indices, shape = x.indices, x.spatial_shape
         M = [0] * L
         subm, down, inv = [None] * L, [None] * L, [None] * L
-        for lvl in range(L):
-            M[lvl] = indices.size(0)
-            kk = self.key_of_level.get(lvl, (None, None))
-            rb = x.indice_dict.get(kk[0]) if kk[0] is not None else None
+        level_idx = [None] * L   # (indices, spatial shape) per level
+        arenas = []
+        ptrs = [0] * len(self.bufs)
+        bufs_of_level = [[] for _ in range(L)]
+        for b, (level, width) in enumerate(self.bufs):
+            bufs_of_level[level].append((b, width))
+
+        def open_level(k):
+            if k == 0:
+                indices, shape = x.indices, x.spatial_shape
+            else:
+                pidx, pshape = level_idx[k - 1]
+                key = self.key_of_level.get(k - 1, (None, None))[1]
+                rd = x.indice_dict.get(key) if key is not None else None
+                if rd is None:
+                    out_indices, mp, inv_mp, out_shape = core.build_down_map(pidx, pshape)
+                    rd = {'kind': 'down', 'map': mp, 'inv_map': inv_mp, 'out_indices': out_indices, 'out_shape': out_shape,
+                          'in_indices': pidx, 'in_shape': pshape}
+                    if key is not None:
+                        x.indice_dict[key] = rd
+                down[k - 1], inv[k - 1] = rd['map'], rd['inv_map']
+                indices, shape = rd['out_indices'], rd['out_shape']
+            level_idx[k] = (indices, shape)
+            M[k] = indices.size(0)
+            key = self.key_of_level.get(k, (None, None))[0]
+            rb = x.indice_dict.get(key) if key is not None else None
             if rb is None:
                 rb = {'kind': 'subm', 'map': core.build_subm_map(indices)}
-                if kk[0] is not None:
-                    x.indice_dict[kk[0]] = rb
-            subm[lvl] = rb['map']
-            if lvl + 1 < L:
-                rd = x.indice_dict.get(kk[1]) if kk[1] is not None else None
-                if rd is None:
-                    out_indices, mp, inv_mp, out_shape = core.build_down_map(indices, shape)
-                    rd = {'kind': 'down', 'map': mp, 'inv_map': inv_mp, 'out_indices': out_indices, 'out_shape': out_shape,
-                          'in_indices': indices, 'in_shape': shape}
-                    if kk[1] is not None:
-                        x.indice_dict[kk[1]] = rd
-                down[lvl], inv[lvl] = rd['map'], rd['inv_map']
-                indices, shape = rd['out_indices'], rd['out_shape']
-        # one arena for every intermediate buffer
-        offs, total = [], 0
-        for level, width in self.bufs:
-            offs.append(total)
-            total += (M[level] * width + 63) // 64 * 64
-        arena = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
-        base = arena.data_ptr()
-        ptrs = [base + 4 * o for o in offs]
-        ptrs[self.in_buf] = feats.data_ptr()
-        c_bufs = (ctypes.c_void_p * len(ptrs))(*ptrs)
-        mk = lambda lst: (ctypes.c_void_p * L)(*[(t.data_ptr() if t is not None else None) for t in lst])  # noqa: E731
-        c_M = (ctypes.c_int * L)(*M)
-        with profiler.record('unet_run', 0):
-            check(_lib.lib().sgb_unet_run(self._c_ops, len(self.ops), c_bufs, mk(subm), mk(down), mk(inv), c_M, L, core._stream()),
-                  'sgb_unet_run')
+                if key is not None:
+                    x.indice_dict[key] = rb
+            subm[k] = rb['map']
+            total, offs = 0, []
+            for b, width in bufs_of_level[k]:
+                offs.append(total)
+                total += (M[k] * width + 63) // 64 * 64
+            arena = torch.empty(max(total, 1), dtype=torch.float32, device=dev)  # one arena per level
+            arenas.append(arena)
+            for (b, width), o in zip(bufs_of_level[k], offs):
+                ptrs[b] = arena.data_ptr() + 4 * o
+
+        opened = -1
+        lib = _lib.lib()
+        for (i0, i1, need) in self.segments:
+            while opened < need:
+                opened += 1
+                open_level(opened)
+            ptrs[self.in_buf] = feats.data_ptr()
+            c_bufs = (ctypes.c_void_p * len(ptrs))(*[p or None for p in ptrs])
+            mk = lambda lst: (ctypes.c_void_p * L)(*[(t.data_ptr() if t is not None else None) for t in lst])  # noqa: E731
+            c_M = (ctypes.c_int * L)(*M)
+            seg = ctypes.cast(ctypes.byref(self._c_ops, i0 * ctypes.sizeof(UnetOp)), ctypes.c_void_p)
+            with profiler.record('unet_run', 0):
+                check(lib.sgb_unet_run(seg, i1 - i0, c_bufs, mk(subm), mk(down), mk(inv), c_M, L, core._stream()), 'sgb_unet_run')
         o = self.out
-        width = self.bufs[o.buf][1]
-        res = arena[offs[o.buf]:offs[o.buf] + M[self.bufs[o.buf][0]] * width].view(M[self.bufs[o.buf][0]], width)
-        res = res[:, o.off:o.off + o.C]
-        res._sgb_arena = arena  # keeps the arena alive as long as the view
+        level, width = self.bufs[o.buf]
+        base = ptrs[o.buf]
+        arena = arenas[level]
+        off = (base - arena.data_ptr()) // 4
+        res = arena[off:off + M[level] * width].view(M[level], width)[:, o.off:o.off + o.C]
+        res._sgb_arenas = arenas  # the views keep their arena alive; keep the others until the result dies as well
         return res
 
 

@@ -196,11 +196,27 @@ def bfs_cluster_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr
     return cluster_idxs, cluster_offsets
 
 
-# The reference's wrapper returns the clusters on the device of its inputs -- the CPU, it copies the lists there first
-# (softgroup.py:458) -- and later indexes that CPU tensor with a CUDA mask (softgroup.py:570), which PyTorch >= 2 rejects.
-# install_as_reference_backends(keep_clusters_on_gpu=True) sets this switch so that the UNMODIFIED reference model runs on
-# a current PyTorch: clusters then stay on the GPU (where they were computed) whatever device the inputs came from.
-KEEP_CLUSTERS_ON_GPU = False
+# PyTorch >= 2 compatibility of the UNMODIFIED reference model: its bfs_cluster wrapper returns CPU tensors
+# (functions.py:295-301: `.new()` on the CPU inputs of softgroup.py:458) and get_instances later indexes that CPU tensor
+# with a CUDA boolean mask (softgroup.py:570) -- accepted by the PyTorch 1.x the reference was written for, an error today.
+# install_as_reference_backends(torch2_compat=True) makes this wrapper return the same CPU data as a tensor subclass whose
+# indexing moves CUDA index tensors to the host first (what PyTorch 1.x did implicitly). Off by default.
+TORCH2_COMPAT = False
+
+
+class HostIndexTensor(torch.Tensor):
+    """CPU tensor that accepts CUDA index / mask tensors in `t[idx]` by copying them to the host."""
+
+    @staticmethod
+    def __new__(cls, t):
+        return torch.Tensor._make_subclass(cls, t)
+
+    def __getitem__(self, idx):
+        if torch.is_tensor(idx) and idx.is_cuda:
+            idx = idx.cpu()
+        elif isinstance(idx, tuple):
+            idx = tuple(i.cpu() if (torch.is_tensor(i) and i.is_cuda) else i for i in idx)
+        return super().__getitem__(idx)
 
 
 class BFSCluster(Function):
@@ -221,8 +237,10 @@ class BFSCluster(Function):
         if idxs.numel() == 0:
             idxs = torch.zeros(1, dtype=torch.int32, device=sl.device)
         cidx, coff = bfs_cluster_segments(idxs, sl, thr)
-        if on_cpu and not KEEP_CLUSTERS_ON_GPU:
+        if on_cpu:
             cidx, coff = cidx.cpu(), coff.cpu()
+            if TORCH2_COMPAT:
+                cidx = HostIndexTensor(cidx)
         return cidx, coff
 
     @staticmethod

@@ -32,10 +32,15 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope='module')
 def ref_module():
     from oracle import build_ref
+    from softgroup_b200.ops import functions as F
     m = build_ref.import_reference_model()
     if m is None:
         pytest.skip('neither /root/reference nor oracle/_ref/pyref is present (run __graft_entry__.build() first)')
-    return m
+    # install_as_reference_backends(torch2_compat=True): softgroup.py:570 indexes a CPU tensor with a CUDA mask, which the
+    # PyTorch 1.x of the reference accepted and PyTorch >= 2 does not
+    F.TORCH2_COMPAT = True
+    yield m
+    F.TORCH2_COMPAT = False
 
 
 class _Cfg(dict):
