@@ -23,6 +23,7 @@
 // Dropping lo*lo leaves a relative error of ~2^-22 per product, i.e. fp32-grade (the north star's 1e-4 over ~40
 // sequential convolutions rules out plain TF32/fp16).
 #include <algorithm>
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -30,6 +31,13 @@
 #include "tcgen05.cuh"
 
 namespace sgb {
+
+// spconv_ss.cu: persistent shared-memory-ring kernel (large levels)
+bool spconv_ss_plan(int K, int Mout, int Cin, int Cout, int sms, int *out);
+int spconv_ss_launch(const float *d_in_pk, int in_stride, const int32_t *d_map, int K, int Mout, const float *d_Wp, int Cin,
+                     int Cout, const float *d_residual, int res_stride, int res_off, const float *d_bias, float *d_out,
+                     int out_stride, int out_off, float *d_pk_out, int pk_stride, int pk_coff, const float *d_pk_scale,
+                     const float *d_pk_shift, int pk_relu, int pk_fill, int *d_oflow, int sms, bool *attr_set, cudaStream_t stream);
 
 constexpr int TC_ROWS = 128;
 constexpr int TC_KC = 32;  // channels per stage
@@ -40,6 +48,7 @@ constexpr int TC_THREADS = 320;  // 8 producer warps + 1 MMA warp + 1 weight-loa
 // lo normal down to |x| = 2^-14 (sgb_spconv_lo_shift() tells the host weight packer).
 constexpr int kLoShift = 11;
 constexpr float kLoScale = (float)(1 << kLoShift), kLoInv = 1.0f / kLoScale;
+static_assert(kLoShift == 11, "spconv_ss.cu hard-codes the remainder scale 2^11");
 constexpr int BAR_FULL = 0, BAR_FREE = 3, BAR_BFULL = 9;  // per pair stage (<= 3); bars[8] = accumulator done
 
 struct TcArgs {
@@ -516,7 +525,7 @@ namespace {
 
 int *g_oflow[16] = {nullptr};  // per device: flag raised by the packing code when a value leaves the fp16 range
 
-struct DevInfo { int sms; bool attr_set; };
+struct DevInfo { int sms; bool attr_set; bool ss_attr_set; };
 DevInfo g_dev[16] = {};
 
 int current_device(int *dev) {
@@ -536,6 +545,21 @@ int ensure_device(int dev) {
     SGB_CUDA_CHECK(cudaMemset(g_oflow[dev], 0, 4));
   }
   return SGB_OK;
+}
+
+// Which kernel runs a problem (launch-by-launch A/B inside the real 150k-point step, profiles/r2_conv_launch_ab.txt): the
+// persistent shared-memory-ring kernel (spconv_ss.cu) wins from 16 row tiles upwards when Cout >= 64 (levels 1-4 of the
+// U-Net: -5 % ... -40 %) and on the big 32-channel levels; the register-gather kernel keeps the deep levels (a handful of
+// row tiles: column split + split-K clusters) and the 32-channel tiny U-Net (a few hundred tiles, +10 % there).
+// SGB_CONV_SS=0/1 (read once) forces one of them for A/B measurements.
+bool use_ss_kernel(int K, int Mout, int Cin, int Cout, int sms) {
+  static const int forced = [] { const char *e = getenv("SGB_CONV_SS"); return e ? atoi(e) : -1; }();
+  if (forced == 0) return false;
+  int plan[5];
+  if (!spconv_ss_plan(K, Mout, Cin, Cout, sms, plan)) return false;
+  if (forced == 1) return true;
+  const int tiles = div_up(Mout, TC_ROWS);
+  return tiles >= 16 && (Cout >= 64 || tiles >= 4 * sms);
 }
 
 }  // namespace
@@ -646,6 +670,10 @@ int sgb_spconv_forward_tc(const float *d_in_pk, int in_stride, int Min, const in
   if (rc) return rc;
   rc = ensure_device(dev);
   if (rc) return rc;
+  if (use_ss_kernel(K, Mout, Cin, Cout, g_dev[dev].sms))
+    return spconv_ss_launch(d_in_pk, in_stride, d_map, K, Mout, d_Wp, Cin, Cout, d_residual, res_stride, res_off, d_bias, d_out,
+                            out_stride, out_off, d_pk_out, pk_stride, pk_coff, d_pk_scale, d_pk_shift, pk_relu, pk_fill,
+                            g_oflow[dev], g_dev[dev].sms, &g_dev[dev].ss_attr_set, (cudaStream_t)stream);
   int plan[6];
   rc = sgb_spconv_tc_plan(K, Mout, Cin, Cout, d_map != nullptr, g_dev[dev].sms, plan);
   if (rc) return rc;

@@ -296,13 +296,37 @@ class SoftGroup(nn.Module):
         return dict(c) if isinstance(c, dict) else {k: getattr(c, k) for k in ('scale', 'spatial_shape') if hasattr(c, k)}
 
     # ------------------------------------------------------------------------------------------------------
+    def _weights_version(self):
+        """Changes whenever a parameter or buffer is written in place (load_state_dict, init, optimizer) or replaced (.cuda(),
+        .to(), .float() go through _apply and drop the cached tensor list). Walking the module tree costs ~1 ms per call on
+        this model (two calls per scan: backbone and tiny U-Net); the tensor list is therefore cached and only the in-place
+        version counters and storage addresses are read per call."""
+        ts = self.__dict__.get('_plan_tensors')
+        if ts is None:
+            ts = [t for t in list(self.parameters()) + list(self.buffers())]
+            self.__dict__['_plan_tensors'] = ts
+        v = 0
+        for t in ts:
+            v += t._version
+        return (v, ts[0].data_ptr() if ts else 0, len(ts))
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_plan_tensors', None)
+        self._plans = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__.pop('_plan_tensors', None)
+        self._plans = {}
+        return super().load_state_dict(*args, **kwargs)
+
     def _run_stack(self, name, input_conv, unet, output_layer, x):
         """input_conv -> unet -> output_layer on SparseConvTensor x -> fp32 feature rows. Compiled plan (one C call) when
         use_plan is set and the tensor path applies, else the module path."""
         from ..spconv import core
         if (self.use_plan and core.CONV_IMPL == 'tc' and x.features.is_cuda and not self.training and
                 max(unet.nPlanes) <= 256):
-            ver = sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+            ver = self._weights_version()
             hit = self._plans.get(name)
             if hit is None or hit[0] != ver:
                 from .unet_plan import compile_backbone
