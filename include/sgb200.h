@@ -238,6 +238,33 @@ int sgb_spconv_forward_tc(const float *d_in_pk, int in_stride, int Min, const in
                           const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
                           int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill,
                           void *stream);
+/* Two kernels implement sgb_spconv_forward_tc with bit-identical results (same products, same accumulation order):
+ *   0 = register gather (spconv_tc.cu: rows -> registers -> tensor memory, column split and split-K clusters for the deep
+ *       U-Net levels), 1 = persistent shared-memory ring (spconv_ss.cu: cp.async row gather into SWIZZLE_128B tiles, one
+ *       CTA per SM walking the row tiles, accumulators double-buffered in tensor memory).
+ * sgb_spconv_kernel_choice: which one sgb_spconv_forward_tc runs for a problem size (sms <= 0: 148).
+ * sgb_spconv_forward_tc_ex: the same call with the kernel named explicitly (-1 = choose) -- parity tests and A/B tools. */
+int sgb_spconv_kernel_choice(int K, int Mout, int Cin, int Cout, int sms);
+int sgb_spconv_forward_tc_ex(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
+                             const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
+                             const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
+                             int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill, int kernel,
+                             void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-class point selection in front of the ball query, all classes in one pass (grouping.cu) -- replaces the loop body
+ * softgroup/model/softgroup.py:430-446 (`(scores[:, class_id] > score_thr).nonzero()`, the `min_npoint` skip, the gathers
+ * of batch_idxs / coords_float / pt_offsets) for the classes h_classes[0..nc) (host array, nc <= 32):
+ *   entries in class-major, ascending point order: d_pts[e] = point, d_seg[e] = rank(class) * B + batch_idxs[point],
+ *   d_shifted[e] = coords[point] + offsets[point] (fp32), all with capacity N * nc; d_seg_offsets int32 [nc*B + 1] =
+ *   first entry of every (class, batch item) segment; d_total int32 [1 + nc] = number of entries, then entries per class
+ *   (0 for a class below min_npoint). d_scores = softmax scores [N][C]. No host synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_group_entries_workspace_bytes(int N, int nc, int B);
+int sgb_group_entries(const float *d_scores, int N, int C, const int *h_classes, int nc, float score_thr, int min_npoint,
+                      const int32_t *d_batch_idxs, int B, const float *d_coords, const float *d_offsets, int32_t *d_pts,
+                      int32_t *d_seg, float *d_shifted, int32_t *d_seg_offsets, int32_t *d_total, void *d_ws, size_t ws_bytes,
+                      void *stream);
 
 /* y[i, c] = max(x[i, c]*scale[c] + shift[c], 0) (relu != 0) -- BatchNorm1d(eval)+ReLU over rows. */
 int sgb_bn_relu(const float *d_x, int x_stride, const float *d_scale, const float *d_shift, int relu, float *d_y,

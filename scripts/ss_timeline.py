@@ -1,7 +1,7 @@
 """Per-level A/B of the two convolution kernels (register-gather spconv_tc_kernel vs persistent shared-memory-ring
 spconv_ss_kernel) on the rulebooks of the 150k-point bench scan, with the per-role wait counters of CTA 0 of the ss kernel
-(development build: scripts/build_ss_timeline.sh). The two kernels run in two PROCESSES (SGB_CONV_SS is read once);
-outputs are compared through a file.
+(development build: scripts/build_ss_timeline.sh). The two kernels run in two PROCESSES (the development library is
+only loaded for the ss leg); outputs are compared through a file.
 Usage: python scripts/ss_timeline.py            (driver: runs both children, prints the table)
        python scripts/ss_timeline.py child 0|1  (one kernel; writes /tmp/ss_ab_<k>.pt)"""
 import os
@@ -18,7 +18,6 @@ NAMES = ['gather:wait_map', 'gather:wait_empty', 'gather:wait_copies', 'iteratio
 
 
 def child(which):
-    os.environ['SGB_CONV_SS'] = str(which)
     from softgroup_b200.ops import _lib
     tl = os.path.join('scripts', 'experiments', 'build', 'libsgb200_tl.so')
     use_tl = which == 1 and os.path.exists(tl) and '--no-tl' not in sys.argv
@@ -58,8 +57,8 @@ def child(which):
         pk = core.act_pack(x, C, 0, C)
 
         def run():
-            check(L.sgb_spconv_forward_tc(ptr(pk), C, M, ptr(mp), 27, M, ptr(W.tc()), C, C, None, 0, 0, None, ptr(out), C, 0,
-                                          None, 0, 0, None, None, 0, 0, core._stream()))
+            check(L.sgb_spconv_forward_tc_ex(ptr(pk), C, M, ptr(mp), 27, M, ptr(W.tc()), C, C, None, 0, 0, None, ptr(out), C, 0,
+                                             None, 0, 0, None, None, 0, 0, which, core._stream()))
         for _ in range(2):
             run()
         ts = []

@@ -551,13 +551,9 @@ int ensure_device(int dev) {
 // persistent shared-memory-ring kernel (spconv_ss.cu) wins from 16 row tiles upwards when Cout >= 64 (levels 1-4 of the
 // U-Net: -5 % ... -40 %) and on the big 32-channel levels; the register-gather kernel keeps the deep levels (a handful of
 // row tiles: column split + split-K clusters) and the 32-channel tiny U-Net (a few hundred tiles, +10 % there).
-// SGB_CONV_SS=0/1 (read once) forces one of them for A/B measurements.
 bool use_ss_kernel(int K, int Mout, int Cin, int Cout, int sms) {
-  static const int forced = [] { const char *e = getenv("SGB_CONV_SS"); return e ? atoi(e) : -1; }();
-  if (forced == 0) return false;
   int plan[5];
   if (!spconv_ss_plan(K, Mout, Cin, Cout, sms, plan)) return false;
-  if (forced == 1) return true;
   const int tiles = div_up(Mout, TC_ROWS);
   return tiles >= 16 && (Cout >= 64 || tiles >= 4 * sms);
 }
@@ -648,12 +644,29 @@ int sgb_spconv_tc_plan(int K, int Mout, int Cin, int Cout, int has_map, int sms,
   return SGB_OK;
 }
 
+// 1 = the persistent shared-memory-ring kernel would run this problem, 0 = the register-gather kernel (pure function).
+int sgb_spconv_kernel_choice(int K, int Mout, int Cin, int Cout, int sms) {
+  if (K < 1 || Mout < 1 || Cin < 1 || Cout < 1) return 0;
+  return use_ss_kernel(K, Mout, Cin, Cout, sms > 0 ? sms : kNumSMs) ? 1 : 0;
+}
+
 int sgb_spconv_forward_tc(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
                           const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
                           const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
                           int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill,
                           void *stream) {
+  return sgb_spconv_forward_tc_ex(d_in_pk, in_stride, Min, d_map, K, Mout, d_Wp, Cin, Cout, d_residual, res_stride, res_off, d_bias,
+                                  d_out, out_stride, out_off, d_pk_out, pk_stride, pk_coff, d_pk_scale, d_pk_shift, pk_relu, pk_fill,
+                                  -1, stream);
+}
+
+int sgb_spconv_forward_tc_ex(const float *d_in_pk, int in_stride, int Min, const int32_t *d_map, int K, int Mout,
+                             const float *d_Wp, int Cin, int Cout, const float *d_residual, int res_stride, int res_off,
+                             const float *d_bias, float *d_out, int out_stride, int out_off, float *d_pk_out, int pk_stride,
+                             int pk_coff, const float *d_pk_scale, const float *d_pk_shift, int pk_relu, int pk_fill, int kernel,
+                             void *stream) {
   if (Mout == 0 || Cout == 0) return SGB_OK;
+  SGB_REQUIRE(kernel >= -1 && kernel <= 1, SGB_ERR_ARG, "kernel: -1 (choose), 0 (register gather), 1 (shared-memory ring)");
   SGB_REQUIRE(d_in_pk && d_Wp && (d_out || d_pk_out) && K >= 1 && K <= 27 && Mout > 0 && Min > 0 && Cin > 0 && Cout > 0, SGB_ERR_ARG,
               "spconv_forward_tc arguments");
   SGB_REQUIRE(d_map || (K == 1 && Min >= Mout), SGB_ERR_ARG, "identity map requires K == 1");
@@ -670,7 +683,7 @@ int sgb_spconv_forward_tc(const float *d_in_pk, int in_stride, int Min, const in
   if (rc) return rc;
   rc = ensure_device(dev);
   if (rc) return rc;
-  if (use_ss_kernel(K, Mout, Cin, Cout, g_dev[dev].sms))
+  if (kernel == 1 || (kernel == -1 && use_ss_kernel(K, Mout, Cin, Cout, g_dev[dev].sms)))
     return spconv_ss_launch(d_in_pk, in_stride, d_map, K, Mout, d_Wp, Cin, Cout, d_residual, res_stride, res_off, d_bias, d_out,
                             out_stride, out_off, d_pk_out, pk_stride, pk_coff, d_pk_scale, d_pk_shift, pk_relu, pk_fill,
                             g_oflow[dev], g_dev[dev].sms, &g_dev[dev].ss_attr_set, (cudaStream_t)stream);

@@ -21,7 +21,8 @@ import torch
 import torch.nn as nn
 
 from .. import spconv
-from ..ops import (ball_query, ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, sec_max, sec_min, voxelization,
+from ..ops import (ball_query, ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, group_entries, sec_max, sec_min,
+                   voxelization,
                    voxelization_idx)
 from ..ops import instances as inst_ops
 from ..util import cuda_cast, force_fp32, rle_encode_ids
@@ -257,7 +258,7 @@ class SoftGroup(nn.Module):
                 coords_float = voxelization(coords_float.contiguous(), p2v_map.contiguous())
             proposals_idx, proposals_offset = self.forward_grouping(semantic_scores, pt_offsets, batch_idxs,
                                                                     coords_float, self.grouping_cfg,
-                                                                    lvl_fusion=lvl_fusion)
+                                                                    lvl_fusion=lvl_fusion, batch_size=int(batch_size))
             self._mark('grouping')
             inst_feats, inst_map = self.clusters_voxelization(proposals_idx, proposals_offset, output_feats,
                                                               coords_float, **self._voxel_cfg())
@@ -395,12 +396,13 @@ class SoftGroup(nn.Module):
     # ------------------------------------------------------------------------------------------------------
     @force_fp32(apply_to=('semantic_scores, pt_offsets'))
     def forward_grouping(self, semantic_scores, pt_offsets, batch_idxs, coords_float, grouping_cfg=None,
-                         lvl_fusion=False):
+                         lvl_fusion=False, batch_size=None):
         """softgroup.py:411-480, all classes in one segmented launch. Returns CUDA int32 tensors
         proposals_idx [sumNPoint,2] (proposal id, point idx), proposals_offset [nProposal+1]."""
         g = self.grouping_cfg
         dev = semantic_scores.device
-        batch_size = int(batch_idxs.max().item()) + 1
+        if batch_size is None:  # softgroup.py:415 reads it back from the device; forward_test knows it from the collated batch
+            batch_size = int(batch_idxs.max().item()) + 1
         scores = semantic_scores.softmax(dim=-1)
         radius = float(self._cfg(g, 'radius'))
         mean_active = int(self._cfg(g, 'mean_active'))
@@ -417,28 +419,25 @@ class SoftGroup(nn.Module):
         empty = (torch.zeros((0, 2), dtype=torch.int32, device=dev), torch.zeros((0, ), dtype=torch.int32, device=dev))
         if not classes:
             return empty
-        cls_t = torch.tensor(classes, device=dev)
-        mask = scores[:, cls_t] > score_thr  # [N, nc]
-        counts = mask.sum(0)
-        keep = counts >= min_npoint  # `object_idxs.size(0) < min_npoint -> continue` (:437-439)
-        mask = mask & keep[None, :]
-        ent = mask.t().nonzero()  # class-major, ascending point index: (class rank, point)
-        n = ent.size(0)
+        # every class of the loop :430-446 in one pass (csrc/grouping.cu): entries (class rank, point) in class-major,
+        # ascending point order, their ball-query segments rank(c) * B + b and shifted coordinates; classes below min_npoint
+        # are dropped like `object_idxs.size(0) < min_npoint -> continue` (:437-439)
+        pts, seg, shifted, seg_offsets, total = group_entries(scores, classes, score_thr, min_npoint, batch_idxs,
+                                                              batch_size, coords_float, pt_offsets)
+        n = int(total[0].item())  # the one host synchronisation of the selection (the list buffers are sized from it)
         if n == 0:
             return empty
-        crank = ent[:, 0]
-        pts = ent[:, 1]
-        seg = (crank * batch_size + batch_idxs[pts].long()).int().contiguous()
-        nseg = len(classes) * batch_size
-        seg_counts = torch.bincount(seg.long(), minlength=nseg)
-        seg_offsets = torch.zeros(nseg + 1, dtype=torch.int32, device=dev)
-        seg_offsets[1:] = seg_counts.cumsum(0).int()
-        shifted = (coords_float[pts] + pt_offsets[pts]).contiguous()
+        pts, seg, shifted = pts[:n], seg[:n], shifted[:n]
         neighbor_inds, start_len, n_active = ballquery_batch_p_nosync(shifted, seg, seg_offsets, radius)
         # per-segment thresholds: threshold*mean or absolute when mean == -1 (bfs_cluster.cpp:70-77), float32 math
-        thr_c = torch.tensor([npoint_thr if cnm[c] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[c]))
-                              for c in classes], dtype=torch.float32, device=dev)
-        seg_thr = thr_c.repeat_interleave(batch_size).contiguous()
+        key = (tuple(classes), batch_size, npoint_thr, str(dev))
+        hit = self.__dict__.get('_seg_thr_cache')
+        if hit is None or hit[0] != key:
+            thr_c = [npoint_thr if cnm[c] == -1 else float(np.float32(npoint_thr) * np.float32(cnm[c])) for c in classes]
+            seg_thr = torch.tensor(np.repeat(np.asarray(thr_c, np.float32), batch_size), dtype=torch.float32, device=dev)
+            hit = (key, seg_thr)
+            self.__dict__['_seg_thr_cache'] = hit
+        seg_thr = hit[1]
         # lists that hit the 1000 cap make the graph asymmetric: the labelling is the exact directed one
         cidx, coff = bfs_cluster_segments(neighbor_inds, start_len, 0.0, node_seg=seg, seg_thr=seg_thr,
                                           nactive=n_active[0:1], upstream_err=n_active[1:2])

@@ -58,6 +58,12 @@ SIGNATURES = {
     'sgb_act_pack': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     'sgb_spconv_forward_tc': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
                                       c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    'sgb_spconv_forward_tc_ex': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
+                                         c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
+    'sgb_spconv_kernel_choice': (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    'sgb_group_entries_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'sgb_group_entries': (c_int, [_P, c_int, c_int, _INTP, c_int, c_float, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  c_size_t, _P]),
     'sgb_unet_run': (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, _P]),
     'sgb_bn_relu': (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     'sgb_gather_rows': (c_int, [_P, _P, _P, c_int, c_int, _P]),

@@ -163,6 +163,35 @@ def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
     return idx, start_len, total
 
 
+def group_entries(scores, classes, score_thr, min_npoint, batch_idxs, batch_size, coords_float, pt_offsets):
+    """All classes of the grouping loop (softgroup/model/softgroup.py:430-446) in one pass on the device: entries in
+    class-major, ascending point order. scores: softmax scores [N, C]; classes: list of class ids (<= 32).
+    Returns (pts int32 [cap], seg int32 [cap], shifted float32 [cap, 3], seg_offsets int32 [nc*B+1], total int32 [1+nc]) with
+    cap = N * len(classes); only the first total[0] entries are meaningful. No host synchronisation."""
+    L = _lib.lib()
+    dev = scores.device
+    N, C = scores.shape
+    nc = len(classes)
+    cap = max(N * nc, 1)
+    pts = torch.empty(cap, dtype=torch.int32, device=dev)
+    seg = torch.empty(cap, dtype=torch.int32, device=dev)
+    shifted = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+    seg_offsets = torch.empty(nc * batch_size + 1, dtype=torch.int32, device=dev)
+    total = torch.empty(1 + nc, dtype=torch.int32, device=dev)
+    ws = _ws(L.sgb_group_entries_workspace_bytes(N, nc, batch_size), dev)
+    cls = (ctypes.c_int * nc)(*[int(c) for c in classes])
+    scores = scores.contiguous()
+    batch_idxs = batch_idxs.int().contiguous()
+    coords_float = coords_float.float().contiguous()
+    pt_offsets = pt_offsets.float().contiguous()
+    with profiler.record('group_entries', 4 * N * C + 28 * N):
+        check(
+            L.sgb_group_entries(ptr(scores), N, C, cls, nc, float(score_thr), int(min_npoint), ptr(batch_idxs), int(batch_size),
+                                ptr(coords_float), ptr(pt_offsets), ptr(pts), ptr(seg), ptr(shifted), ptr(seg_offsets), ptr(total),
+                                ptr(ws), ws.numel(), _stream()), 'sgb_group_entries')
+    return pts, seg, shifted, seg_offsets, total
+
+
 # ----------------------------------------------------------------------------------------------
 # clustering
 # ----------------------------------------------------------------------------------------------

@@ -147,6 +147,9 @@ def build_down_map(indices, spatial_shape):
 
 
 CONV_IMPL = os.environ.get('SGB_CONV_IMPL', 'tc')  # 'tc' = tcgen05 tensor cores (default), 'ffma' = CUDA-core fp32 (A/B only)
+# which of the two tcgen05 kernels the module path asks for: -1 = the library chooses (sgb_spconv_kernel_choice), 0 = register
+# gather, 1 = persistent shared-memory ring. Parity tests run every case under 0 and 1; the compiled plan always uses -1.
+CONV_KERNEL = -1
 
 
 def pack_weight_tc(W):
@@ -244,10 +247,11 @@ def conv_forward(feats, in_stride, in_off, mp, K, Mout, W, Cin, Cout, act=None, 
             pk_out, pk_stride, pk_coff, es, eh, fill = emit.buf, emit.buf.size(1), emit.coff, emit.scale, emit.shift, int(emit.fill)
         with profiler.record(name, nbytes):
             check(
-                _lib.lib().sgb_spconv_forward_tc(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.tc()), Cin, Cout,
-                                                 ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride or 0, out_off,
-                                                 ptr(pk_out), pk_stride, pk_coff, ptr(es), ptr(eh), 1, fill, _stream()),
-                'sgb_spconv_forward_tc')
+                _lib.lib().sgb_spconv_forward_tc_ex(ptr(pk), pk.size(1), m_in, ptr(mp), K, Mout, ptr(W.tc()), Cin, Cout,
+                                                    ptr(residual), rs, ro, ptr(bias), ptr(out), out_stride or 0, out_off,
+                                                    ptr(pk_out), pk_stride, pk_coff, ptr(es), ptr(eh), 1, fill, CONV_KERNEL,
+                                                    _stream()),
+                'sgb_spconv_forward_tc_ex')
         return (out, pk_out) if emit is not None else out
     with profiler.record(name, nbytes):
         check(

@@ -25,7 +25,8 @@ from softgroup_b200.model import softgroup as sg_module
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, 'golden'))
 from seeded_weights import CFG_OVERRIDES, SCAN, WEIGHT_SEED, fill_seeded, load_calibrated, weights_digest  # noqa: E402
-from test_host_grouping import _fake_ballquery_nosync, _fake_bfs_segments, _fake_sec, _fake_voxelization  # noqa: E402
+from test_host_grouping import (_fake_ballquery_nosync, _fake_bfs_segments, _fake_group_entries, _fake_sec,  # noqa: E402
+                                _fake_voxelization)
 
 
 @pytest.fixture(scope='module')
@@ -67,6 +68,7 @@ def test_oracle_unet_composition_equals_reference_blocks(gold, model):
 def test_forward_grouping_reproduces_reference_proposals(monkeypatch, gold, model):
     monkeypatch.setattr(sg_module, 'ballquery_batch_p_nosync', _fake_ballquery_nosync)
     monkeypatch.setattr(sg_module, 'bfs_cluster_segments', _fake_bfs_segments)
+    monkeypatch.setattr(sg_module, 'group_entries', _fake_group_entries)
     n = gold['semantic_scores'].shape[0]
     scan = synth.make_scan(SCAN['shape'], seed=SCAN['seed'])
     pidx, poff = model.forward_grouping(torch.from_numpy(gold['semantic_scores']), torch.from_numpy(gold['pt_offsets']),

@@ -368,3 +368,27 @@ def test_ballquery_wide_index_range_uses_sort_fallback():
         d2 = (d[:, 2].astype(np.float64) * d[:, 2] + d2).astype(np.float32)
         want = np.where(d2 < np.float32(0.04) * np.float32(0.04))[0][:1000]
         assert np.array_equal(g[s[i, 0]:s[i, 0] + s[i, 1]], want), i
+
+
+@pytest.mark.parametrize('n,batch,min_npoint', [(5000, 1, 0), (40000, 3, 60), (150000, 1, 100), (1, 1, 0)])
+def test_group_entries_equals_reference_loop(n, batch, min_npoint):
+    """csrc/grouping.cu vs the reference's per-class loop (softgroup.py:430-446): entries, segments, shifted coordinates,
+    segment offsets and per-class counts, bit-exact (random scores around the threshold, classes dropped by min_npoint)."""
+    from softgroup_b200.ops import group_entries
+    from test_host_grouping import _fake_group_entries
+    g = torch.Generator().manual_seed(n + batch)
+    C = 20
+    logits = torch.randn(n, C, generator=g) * 2
+    logits[:, 5] -= 6  # a rare class: falls below min_npoint
+    scores = logits.softmax(-1)
+    classes = [c for c in range(C) if c not in (0, 1)]
+    bsz = torch.sort(torch.randint(0, batch, (n, ), generator=g))[0].int()
+    coords, offs = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g) * 0.1
+    want = _fake_group_entries(scores, classes, 0.2, min_npoint, bsz, batch, coords, offs)
+    got = group_entries(scores.cuda(), classes, 0.2, min_npoint, bsz.cuda(), batch, coords.cuda(), offs.cuda())
+    tot = got[4].cpu()
+    assert torch.equal(tot, want[4])
+    m = int(tot[0])
+    assert torch.equal(got[0][:m].cpu(), want[0]) and torch.equal(got[1][:m].cpu(), want[1])
+    assert torch.equal(got[2][:m].cpu(), want[2])
+    assert torch.equal(got[3].cpu(), want[3])

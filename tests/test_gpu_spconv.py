@@ -20,6 +20,17 @@ def _cuda(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+@pytest.fixture(params=[0, 1], ids=['register_gather', 'smem_ring'])
+def conv_kernel(request):
+    """Every single-convolution parity case runs under both tcgen05 kernels (spconv_tc.cu / spconv_ss.cu), named explicitly
+    through sgb_spconv_forward_tc_ex, whatever sgb_spconv_kernel_choice would pick for the size."""
+    from softgroup_b200.spconv import core
+    old = core.CONV_KERNEL
+    core.CONV_KERNEL = request.param
+    yield request.param
+    core.CONV_KERNEL = old
+
+
 def _case(seed, shape=(23, 18, 15), B=2, C=8, density=0.2):
     rng = np.random.RandomState(seed)
     idx = []
@@ -66,7 +77,7 @@ def test_rulebook_full_size():
 
 
 @pytest.mark.parametrize('Cin,Cout', [(6, 32), (32, 32), (64, 32), (96, 128), (16, 48), (224, 224)])
-def test_subm_conv_vs_oracle(Cin, Cout):
+def test_subm_conv_vs_oracle(Cin, Cout, conv_kernel):
     idx, feats, _, _ = _case(Cin + Cout, C=Cin, density=0.25)
     rng = np.random.RandomState(2)
     W = (rng.randn(Cout, 3, 3, 3, Cin) / np.sqrt(27 * Cin)).astype(np.float32)
@@ -111,7 +122,7 @@ def _rel_elem(got, want):
 
 @pytest.mark.parametrize('Cin,Cout,n_rows', [(32, 32, 40000), (64, 64, 24000), (96, 96, 24000), (128, 128, 20000),
                                              (192, 96, 20000), (64, 32, 40000), (224, 224, 20000)])
-def test_subm_conv_bench_tile_configs_vs_oracle(Cin, Cout, n_rows):
+def test_subm_conv_bench_tile_configs_vs_oracle(Cin, Cout, n_rows, conv_kernel):
     """The tile configurations the 150k-point bench actually runs (>= 148 row tiles, so no column shrink / split-K of
     the small cases above): compared with the float64-accumulating oracle PER ELEMENT at the north-star tolerance."""
     idx = _surface_case(Cin * 7 + Cout, n_rows)
@@ -132,7 +143,7 @@ def test_subm_conv_bench_tile_configs_vs_oracle(Cin, Cout, n_rows):
     assert _rel_elem(got, want) < 1e-4
 
 
-def test_conv_fused_act_residual_bias_strided():
+def test_conv_fused_act_residual_bias_strided(conv_kernel):
     idx, feats, _, _ = _case(5, C=40)
     rng = np.random.RandomState(3)
     M = len(idx)
@@ -152,7 +163,7 @@ def test_conv_fused_act_residual_bias_strided():
     assert np.all(got[:, :32] == 7.0) and np.all(got[:, 56:] == 7.0)
 
 
-def test_down_and_inverse_modules():
+def test_down_and_inverse_modules(conv_kernel):
     idx, feats, shape, B = _case(7, C=32)
     rng = np.random.RandomState(4)
     Wd = (rng.randn(64, 2, 2, 2, 32) / 16).astype(np.float32)
@@ -236,3 +247,38 @@ def test_plan_equals_module_path(channels, num_blocks, n):
     a = run(True, 'tiny', None, model.tiny_unet, model.tiny_unet_outputlayer, tf, _cuda(occ), [20, 20, 20], 5)
     b = run(False, 'tiny', None, model.tiny_unet, model.tiny_unet_outputlayer, tf, _cuda(occ), [20, 20, 20], 5)
     assert torch.equal(a, b)
+
+
+def test_both_conv_kernels_bit_identical_and_choice():
+    """The two tcgen05 kernels evaluate the same products in the same order: bit-identical rows at a bench-size level
+    (residual + bias + packed twin output), and sgb_spconv_kernel_choice follows the documented rule."""
+    from softgroup_b200.ops import _lib
+    from softgroup_b200.spconv import core
+    L = _lib.lib()
+    assert L.sgb_spconv_kernel_choice(27, 137100, 32, 32, 148) == 1    # level 0: >= 4 * 148 row tiles
+    assert L.sgb_spconv_kernel_choice(27, 42391, 96, 96, 148) == 1     # level 2
+    assert L.sgb_spconv_kernel_choice(27, 1933, 160, 160, 148) == 1    # level 4: 16 row tiles is the threshold
+    assert L.sgb_spconv_kernel_choice(27, 1900, 160, 160, 148) == 0
+    assert L.sgb_spconv_kernel_choice(27, 332, 192, 192, 148) == 0     # deep level: split-K clusters
+    assert L.sgb_spconv_kernel_choice(27, 36000, 32, 32, 148) == 0     # 32-channel tiny U-Net
+    idx = _surface_case(11, 30000)
+    rng = np.random.RandomState(5)
+    Cin, Cout = 96, 64
+    M = len(idx)
+    feats = rng.randn(M, Cin).astype(np.float32)
+    W = (rng.randn(Cout, 3, 3, 3, Cin) / np.sqrt(12 * Cin)).astype(np.float32)
+    res, bias = rng.randn(M, Cout).astype(np.float32), rng.randn(Cout).astype(np.float32)
+    mp = _cuda(so.subm_map(idx))
+    wk = torch.from_numpy(W.reshape(Cout, 27, Cin).transpose(1, 2, 0).copy()).cuda()
+    outs = []
+    old = core.CONV_KERNEL
+    try:
+        for k in (0, 1):
+            core.CONV_KERNEL = k
+            emit = core.Emit(_cuda(rng.rand(Cout).astype(np.float32) * 0 + 1.5), _cuda(np.full(Cout, -0.25, np.float32)), key=None)
+            y, pk = spconv.conv_forward(_cuda(feats), Cin, 0, mp, 27, M, wk, Cin, Cout, residual=_cuda(res), bias=_cuda(bias), emit=emit)
+            outs.append((y.clone(), pk.clone()))
+    finally:
+        core.CONV_KERNEL = old
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1].view(torch.int32), outs[1][1].view(torch.int32))

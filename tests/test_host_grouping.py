@@ -19,6 +19,26 @@ def _fake_ballquery_nosync(coords, batch_idxs, batch_offsets, radius):
             torch.tensor([idx.size, 0], dtype=torch.int32))
 
 
+def _fake_group_entries(scores, classes, score_thr, min_npoint, batch_idxs, batch_size, coords_float, pt_offsets):
+    """CPU stand-in of csrc/grouping.cu written as the reference's own per-class loop (softgroup.py:430-446)."""
+    pts, seg, counts = [], [], []
+    for r, c in enumerate(classes):
+        obj = (scores[:, c] > score_thr).nonzero().view(-1)
+        if obj.size(0) < min_npoint:
+            counts.append(0)
+            continue
+        counts.append(obj.size(0))
+        pts.append(obj)
+        seg.append(r * batch_size + batch_idxs[obj].long())
+    pts = torch.cat(pts).int() if pts else torch.zeros(0, dtype=torch.int32)
+    seg = torch.cat(seg).int() if seg else torch.zeros(0, dtype=torch.int32)
+    shifted = coords_float[pts.long()] + pt_offsets[pts.long()]
+    seg_offsets = torch.zeros(len(classes) * batch_size + 1, dtype=torch.int32)
+    seg_offsets[1:] = torch.bincount(seg.long(), minlength=len(classes) * batch_size).cumsum(0).int()
+    total = torch.tensor([pts.numel()] + counts, dtype=torch.int32)
+    return pts, seg, shifted, seg_offsets, total
+
+
 def _fake_bfs_segments(ball_query_idxs, start_len, thr, node_seg=None, seg_thr=None, nactive=None, upstream_err=None):
     """bfs_cluster.cpp:33-126 over the whole node set with a per-seed-segment threshold (what the library computes)."""
     idxs, sl = ball_query_idxs.numpy(), start_len.numpy()
@@ -83,6 +103,7 @@ def reference_forward_grouping(model, semantic_scores, pt_offsets, batch_idxs, c
 def test_forward_grouping_equals_reference_loop(monkeypatch, seed, batch):
     monkeypatch.setattr(sg_module, 'ballquery_batch_p_nosync', _fake_ballquery_nosync)
     monkeypatch.setattr(sg_module, 'bfs_cluster_segments', _fake_bfs_segments)
+    monkeypatch.setattr(sg_module, 'group_entries', _fake_group_entries)
     model = SoftGroup(**model_cfg('scannet', channels=16, num_blocks=2, test_cfg=dict(min_npoint=30))).eval()
     parts = [synth.make_scan('c1_plumbing', seed=seed * 10 + b, n_points=1500) for b in range(batch)]
     scores, offs, coords, bidx = [], [], [], []
@@ -257,6 +278,7 @@ def test_forward_grouping_equals_reference_method(monkeypatch, ref_model_module)
     monkeypatch.setattr(ref_model_module, 'bfs_cluster', ref_bfs)
     monkeypatch.setattr(sg_module, 'ballquery_batch_p_nosync', _fake_ballquery_nosync)
     monkeypatch.setattr(sg_module, 'bfs_cluster_segments', _fake_bfs_segments)
+    monkeypatch.setattr(sg_module, 'group_entries', _fake_group_entries)
     sc = synth.make_scan('c1_plumbing', seed=7, n_points=2000)
     scores, offs = synth.grouping_inputs(sc, sigma=0.03, seed=7)
     args = [torch.from_numpy(scores), torch.from_numpy(offs), torch.zeros(scores.shape[0], dtype=torch.int32),
