@@ -57,6 +57,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-points', type=int, default=20000)
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--inflight', type=int, default=3,
+                    help='scans in flight per GPU in the timed legs (harness.ScanPipeline); 1 = strictly one after another')
     return ap.parse_args()
 
 
@@ -412,6 +414,16 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one rank per GPU: keep every rank on its own share of the host cores (the GPUs of the 8-GPU box sit four per NUMA
+        # node, in rank order) and torch's intra-op pool small -- the host side of a scan is launch latency, not throughput
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+        except Exception:
+            pass
+        torch.set_num_threads(min(8, max(1, (os.cpu_count() or 8) // world)))
+    if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from softgroup_b200 import harness
@@ -466,12 +478,40 @@ def main():
         ms = sum(a.elapsed_time(b) for a, b in evs)
         return ms, wall, out
 
+    pipe = harness.ScanPipeline(model, workers=args.inflight) if args.inflight > 1 else None
+
+    def timed_inflight(fn, steps, warmup):
+        """`steps` scans with args.inflight of them in flight (one host thread + CUDA stream each, harness.ScanPipeline): the
+        timed region runs from an event every worker stream waits on to an event recorded after all of them; the L2 flush of
+        every scan is INSIDE it (on the scan's own stream)."""
+        with torch.no_grad():
+            def call(_):  # results are dropped at once: a retained result dict pins its host buffers, and every later scan
+                fn()      # would then pay a fresh cudaHostAlloc for its own
+                return None
+            pipe.map(call, range(warmup))
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall = time.perf_counter()
+            e0.record()
+            res, evs = pipe.map(call, range(steps), start_event=e0, before=flush.zero_)
+            for ev in evs:
+                torch.cuda.current_stream().wait_event(ev)
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t_wall
+        return e0.elapsed_time(e1), wall
+
     sampler = ClockSampler(local_rank)
     with sampler:
         l0 = _lib.lib().sgb_launch_count()
-        dev_ms, dev_wall, out = timed(step_device, args.steps, max(args.warmup, 3))
+        seq_dev_ms, dev_wall, out = timed(step_device, args.steps, max(args.warmup, 3))
         launches = (_lib.lib().sgb_launch_count() - l0)
-        e2e_ms, e2e_wall, ret = timed(lambda: harness.run_scan(model, hb, inject_pointwise=inj), args.steps, 2)
+        seq_e2e_ms, e2e_wall, ret = timed(lambda: harness.run_scan(model, hb, inject_pointwise=inj), args.steps, 3)
+        if pipe is not None:
+            dev_ms, dev_wall = timed_inflight(step_device, args.steps, max(args.warmup, 3))
+            e2e_ms, e2e_wall = timed_inflight(lambda: harness.run_scan(model, hb, inject_pointwise=inj), args.steps, 3)
+        else:
+            dev_ms, e2e_ms = seq_dev_ms, seq_e2e_ms
         # instrumented pass (per-op CUDA events) -> dominant kernel and its roofline. It runs the module path (one ctypes call
         # per launch, same kernels and arguments as the compiled plan of the timed legs) so that every launch has its own event
         profiler.reset()
@@ -481,7 +521,7 @@ def main():
     # launches counted over warmup+steps of the first leg -> per timed region
     launches_per_step = launches // (args.steps + max(args.warmup, 3))
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device='cuda')
+    t = torch.tensor([dev_ms, e2e_ms, seq_dev_ms, seq_e2e_ms], dtype=torch.float64, device='cuda')
     per_rank = None
     if world > 1:
         allt = [torch.zeros_like(t) for _ in range(world)]
@@ -490,6 +530,7 @@ def main():
                         e2e_ms_per_step=[round(float(x[1]) / args.steps, 3) for x in allt])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    seq_dev_ms_max, seq_e2e_ms_max = float(t[2]), float(t[3])
     value = world * args.steps / (dev_ms_max / 1e3)
     e2e_value = world * args.steps / (e2e_ms_max / 1e3)
 
@@ -527,12 +568,20 @@ def main():
                                 'outputs are computed, then overwritten by synthetic predictions (one-hot*8+N(0,1), centroid '
                                 'offsets+N(0,sigma)) so grouping sees a trained-checkpoint load' %
                                 (wl['cfg'], cfg['channels'], cfg['num_blocks']),
-                                l2='flushed: 512 MiB memset between timed steps',
+                                l2='flushed: 512 MiB memset before every scan (between the per-step events of the sequential legs; inside the timed '
+                                'region, on the scan\'s own stream, with scans in flight)',
                                 parallelism='dp%d (independent scans, no data-path collective)' % world,
+                                inflight='%d scans in flight per GPU (host thread + CUDA stream each); one at a time: see '
+                                '`sequential`' % args.inflight,
                                 proposals=int(out['proposals_offset'].numel() - 1),
                                 proposal_points=int(out['proposals_idx'].size(0))),
                     e2e=dict(value=e2e_value, unit='scans/sec', h2d_bytes_per_step=harness.h2d_bytes(hb),
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms_max / args.steps),
+                    sequential=dict(note='one scan at a time (latency): device step with inputs resident / end to end from '
+                                    'pinned host tensors', ms_per_step=seq_dev_ms_max / args.steps,
+                                    e2e_ms_per_step=seq_e2e_ms_max / args.steps,
+                                    value=world * args.steps / (seq_dev_ms_max / 1e3),
+                                    e2e_value=world * args.steps / (seq_e2e_ms_max / 1e3)),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     clocks=sampler.summary(), roofline=roofline, stage_ms=prof.get('stage_ms'))
         if per_rank is not None:

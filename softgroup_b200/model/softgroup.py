@@ -15,6 +15,7 @@ What is restructured underneath (same outputs):
     segmented sum, kept masks are encoded to the reference's RLE wire format from sorted point ids.
 """
 import functools
+import threading
 
 import numpy as np
 import torch
@@ -55,9 +56,10 @@ class _HostFetcher(object):
     _streams = {}
 
     def __init__(self, device):
-        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        key = (dev, threading.get_ident())  # one side stream per device and calling thread (scans in flight do not share it)
         if key not in _HostFetcher._streams:
-            _HostFetcher._streams[key] = torch.cuda.Stream(device=key)
+            _HostFetcher._streams[key] = torch.cuda.Stream(device=dev)
         self.stream = _HostFetcher._streams[key]
         self.items = []
 
@@ -153,6 +155,7 @@ class SoftGroup(nn.Module):
         self.use_plan = True
         self._plans = {}
         self.stage_ms = None  # filled when profile_stages is set
+        self._tls = threading.local()  # per-thread scratch of a forward (several scans may be in flight: harness.ScanPipeline)
         self.profile_stages = False
 
     def init_weights(self):
@@ -280,7 +283,7 @@ class SoftGroup(nn.Module):
                     if self.sem2ins_classes or not inst or lvl_fusion:
                         pan = self.panoptic_fusion(semantic_preds.cpu().numpy(), inst)
                     else:  # every instance has its bitmap on the device: paste there (softgroup.py:606-639)
-                        bm, npts = self._last_instance_bitmaps
+                        bm, npts = self._tls.instance_bitmaps
                         pan = self.panoptic_fusion_gpu(semantic_preds, inst, bm, npts)
                     ret.update(panoptic_preds=pan)
         if device_only:
@@ -656,7 +659,7 @@ class SoftGroup(nn.Module):
         conf = score.t()[kc, kp]
         rles = inst_ops.bitmaps_to_rle(bitmaps, num_points)
         kc_np, conf_np = kc.cpu().numpy(), conf.cpu().numpy()
-        self._last_instance_bitmaps = (bitmaps, num_points)  # reused by panoptic_fusion in the same forward
+        self._tls.instance_bitmaps = (bitmaps, num_points)  # reused by panoptic_fusion in the same forward (same thread)
         instances = []
         semantic_pred = None
         k = 0

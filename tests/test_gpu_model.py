@@ -134,6 +134,30 @@ def test_end_to_end_result_dict():
     assert m.shape == (30000, ) and m.sum() >= 100
 
 
+def test_scans_in_flight_equal_sequential_calls():
+    """harness.ScanPipeline (two host threads, one CUDA stream each) returns, in input order, exactly what sequential
+    run_scan calls return: six scans of three different sizes, every result array and every instance (RLE string, label,
+    confidence) identical."""
+    model = _model()
+    scans = [synth.make_scan('c2_scannet', seed=s, n_points=n) for s, n in ((1, 20000), (2, 31000), (3, 26000))] * 2
+    hbs = [harness.to_host_batch(sc) for sc in scans]
+    injs = [harness.pointwise_injection(sc, sigma=0.03, seed=7) for sc in scans]
+    with torch.no_grad():
+        seq = [harness.run_scan(model, hb, inject_pointwise=inj) for hb, inj in zip(hbs, injs)]
+    pipe = harness.ScanPipeline(model, workers=2)
+    try:
+        par = pipe.run_scans(hbs, inject_pointwise=injs)
+    finally:
+        pipe.close()
+    assert len(par) == len(seq)
+    for a, b in zip(seq, par):
+        for k in ('semantic_preds', 'offset_preds', 'gt_instances'):
+            assert np.array_equal(a[k], b[k]), k
+        assert len(a['pred_instances']) == len(b['pred_instances']) and len(a['pred_instances']) > 0
+        for x, y in zip(a['pred_instances'], b['pred_instances']):
+            assert x['label_id'] == y['label_id'] and x['pred_mask'] == y['pred_mask'] and float(x['conf']) == float(y['conf'])
+
+
 def test_x4_split_backbone_vs_oracle():
     """S3DIS path (softgroup.py:380-409): 4 interleaved pieces through the backbone, merged back to point order."""
     from oracle import spconv_oracle as so
