@@ -545,14 +545,16 @@ def main():
         prof = profiler.summary()
         dom = prof['dominant']
         traffic = None
-        try:  # dram__bytes_read+write of the dominant kernel from the committed ncu capture (per step, like achieved)
-            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel_traffic.json')))
-            if tj.get('kernel') == dom['name']:
+        traffic_note = None
+        try:  # dram__bytes_read+write of the conv launches from the committed OFFLINE ncu capture (per step, like achieved)
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_dominant_kernel_traffic.json')))
+            if tj.get('kernel') == dom['name'] and args.workload == 'c2':
                 traffic = tj['dram_bytes_per_step']
+                traffic_note = tj.get('note')
         except Exception:
             pass
         roofline = dict(bound='hbm', kernel=dom['name'], achieved=dom['gbs'], peak=hbm_peak, unit='GB/s',
-                        frac=dom['gbs'] / hbm_peak, traffic=traffic, peak_source=peak_src,
+                        frac=dom['gbs'] / hbm_peak, traffic=traffic, traffic_source=traffic_note, peak_source=peak_src,
                         launches_per_step=dom['launches_per_step'], avg_launch_us=dom['avg_us'],
                         share_of_step=dom['share'], algorithmic_bytes_per_step=dom['bytes_per_step'],
                         by_kernel=prof['by_kernel'])

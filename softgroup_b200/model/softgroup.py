@@ -290,6 +290,8 @@ class SoftGroup(nn.Module):
             ret.update(semantic_preds=semantic_preds, pt_offsets=pt_offsets)
         else:
             ret.update(fetch.finish())
+        if semantic_scores.is_cuda:
+            spconv.check_overflow()  # an activation beyond the fp16 hi/lo range raises here instead of saturating silently
         if self.profile_stages:
             torch.cuda.synchronize()
             self.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._events[:-1], self._events[1:])}

@@ -204,6 +204,19 @@ def act_pack(feats, in_stride, in_off, C, act=None, relu=None, out=None, out_cof
     return out
 
 
+def check_overflow():
+    """The tcgen05 path carries activations as fp16 hi/lo pairs: a packed value beyond the fp16 range (|y| > 65504, or NaN)
+    cannot be represented. The packing code raises a per-device flag instead of saturating silently; this reads and clears
+    it (a blocking 4-byte read on the current stream -- call it where the host waits anyway) and raises."""
+    import ctypes
+    flag = ctypes.c_int(0)
+    check(_lib.lib().sgb_spconv_overflow(ctypes.byref(flag), _stream()), 'sgb_spconv_overflow')
+    if flag.value:
+        raise _lib.SgbError('sparse convolution: an activation left the fp16 range of the hi/lo split (|y| > 65504 or NaN after '
+                            'BatchNorm+ReLU); the tensor-core path cannot represent it -- rescale the checkpoint or run '
+                            'SGB_CONV_IMPL=ffma')
+
+
 class Emit(object):
     """What a producing conv writes besides (or instead of) fp32 rows: the packed rows of ITS CONSUMER's input, i.e.
     relu(y * scale + shift) split into fp16 hi/lo -- the consumer's BatchNorm(eval)+ReLU folded into this epilogue.

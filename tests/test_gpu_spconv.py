@@ -282,3 +282,30 @@ def test_both_conv_kernels_bit_identical_and_choice():
         core.CONV_KERNEL = old
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1].view(torch.int32), outs[1][1].view(torch.int32))
+
+
+def test_activation_beyond_fp16_range_raises(conv_kernel):
+    """|x| > 65504 cannot be carried by the fp16 hi/lo split: the packing code raises a flag and check_overflow() turns it
+    into an exception (no silent saturation) -- from the input packer and from a producing conv's fused epilogue; the flag
+    is cleared by the read, an in-range tensor afterwards passes."""
+    from softgroup_b200.ops._lib import SgbError
+    from softgroup_b200.spconv import core
+    idx, feats, _, _ = _case(3, C=32)
+    M = len(idx)
+    mp = _cuda(so.subm_map(idx))
+    rng = np.random.RandomState(0)
+    wk = torch.from_numpy((rng.randn(27, 32, 32) / 30).astype(np.float32)).cuda()
+    spconv.check_overflow()  # clean state
+    big = feats.copy()
+    big[5, 7] = 1.0e5
+    spconv.conv_forward(_cuda(big), 32, 0, mp, 27, M, wk, 32, 32)  # the input packer sees the value
+    with pytest.raises(SgbError):
+        spconv.check_overflow()
+    spconv.check_overflow()  # cleared
+    # a producing conv whose consumer BatchNorm scales the output beyond the range: flagged by the fused epilogue
+    emit = core.Emit(_cuda(np.full(32, 1.0e7, np.float32)), _cuda(np.zeros(32, np.float32)), key=None)
+    spconv.conv_forward(_cuda(feats), 32, 0, mp, 27, M, wk, 32, 32, emit=emit)
+    with pytest.raises(SgbError):
+        spconv.check_overflow()
+    spconv.conv_forward(_cuda(feats), 32, 0, mp, 27, M, wk, 32, 32)
+    spconv.check_overflow()
