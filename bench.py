@@ -413,16 +413,36 @@ def main():
 
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local_rank)
+    # The host side of a scan is launch latency, not throughput: keep torch's intra-op pool small (a 128-thread pool woken
+    # for tiny CPU ops cost 3 ms per scan end to end) and, with one rank per GPU, give every rank its own share of the cores
+    # of ITS GPU's NUMA node (NVML's ideal CPU affinity; the GPUs of the 8-GPU box sit four per node).
+    torch.set_num_threads(min(8, max(1, (os.cpu_count() or 8) // max(world, 1))))
     if world > 1:
-        # one rank per GPU: keep every rank on its own share of the host cores (the GPUs of the 8-GPU box sit four per NUMA
-        # node, in rank order) and torch's intra-op pool small -- the host side of a scan is launch latency, not throughput
         try:
-            cores = sorted(os.sched_getaffinity(0))
-            per = max(1, len(cores) // world)
-            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+            import pynvml
+            pynvml.nvmlInit()
+            allowed = set(os.sched_getaffinity(0))
+            words = (max(allowed) // 64) + 1
+
+            def cores_of(i):
+                uuid = str(torch.cuda.get_device_properties(i).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+                mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+                return tuple(sorted(c for c in allowed if (mask[c // 64] >> (c % 64)) & 1))
+
+            n_local = min(world, torch.cuda.device_count())
+            sets = [cores_of(i) for i in range(n_local)]
+            mine = sets[local_rank]
+            group = [i for i in range(n_local) if sets[i] == mine]
+            k = group.index(local_rank)
+            os.sched_setaffinity(0, set(mine[k::len(group)]))  # strided: a core and its hyper-thread sibling stay with one rank
         except Exception:
-            pass
-        torch.set_num_threads(min(8, max(1, (os.cpu_count() or 8) // world)))
+            try:  # no NVML: an even split of the allowed cores in rank order
+                cores = sorted(os.sched_getaffinity(0))
+                per = max(1, len(cores) // world)
+                os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+            except Exception:
+                pass
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
