@@ -382,9 +382,10 @@ def main():
             sc['feats'] = sc['feats'][:, :1].copy()
         if wl.get('no_coords'):
             pass  # with_coords=False in the model config: feats stay rgb
+        base = sc
         if wl.get('x4'):
             sc = synth.to_x4_split(sc)
-        return sc
+        return sc, base  # base: the scan in point order = the order of the MERGED x4 outputs the predictions are injected in
 
     if args.impl == 'reference':
         assert args.workload == 'c2', 'the reference arm is defined on the metric configuration (c2)'
@@ -453,9 +454,9 @@ def main():
 
     torch.manual_seed(0)
     model = SoftGroup(**cfg).cuda().eval()
-    scan = make_workload_scan(args.seed + rank)
+    scan, scan_points = make_workload_scan(args.seed + rank)
     hb = harness.to_host_batch(scan, pin=True)
-    inj = harness.pointwise_injection(scan, sigma=wl['sigma'], seed=args.seed + rank, fragments=wl.get('fragments', 1),
+    inj = harness.pointwise_injection(scan_points, sigma=wl['sigma'], seed=args.seed + rank, fragments=wl.get('fragments', 1),
                                       confusion=wl.get('confusion', 0.0))
     dev = harness.device_batch(hb)
     dev_in = {k: v for k, v in dev.items() if k not in ('voxel_coords', 'v2p_map', 'p2v_map')}

@@ -365,8 +365,15 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
           for (int t = 0; t < 4; t++) {
             if (v[t] < 0) continue;
             const unsigned long long mine = hi | (unsigned)(j0 + t * 32 + lane);
-            if (k[t] > mine && ((uint32_t)(k[t] >> 32) != 0xFFFFFFFFu || (uint32_t)k[t] == (uint32_t)seed))
-              atomicMin(&w.key[v[t]], mine);
+            if (k[t] > mine) {
+              // Is v a node of THIS component? An unvisited key carries the label; a visited key does not -- and v may be a
+              // node of ANOTHER component (a directed edge into a component with a smaller seed: lists cut by the 1000 cap)
+              // that a different cluster is emitting right now, whose claim keys must not be lowered from here (round-2
+              // fix: found on the 1.5M-point STPLS3D-shape tile, where components touch). The label array is final.
+              const bool same = ((uint32_t)(k[t] >> 32) == 0xFFFFFFFFu) ? ((uint32_t)k[t] == (uint32_t)seed)
+                                                                        : (ld_ca_i32(&w.label[v[t]]) == seed);
+              if (same) atomicMin(&w.key[v[t]], mine);
+            }
           }
         }
       }

@@ -340,3 +340,60 @@ def test_softgroup_pp_grouping_matches_reference_loop():
     assert np.array_equal(poff.cpu().numpy(), want_off)
     assert np.array_equal(pidx.cpu().numpy(), want_idx)
     assert len(want_off) > 20
+
+
+def test_full_size_stpls3d_tile_clustering_vs_oracle(monkeypatch):
+    """BASELINE config 5 at FULL size (1.5M points, SoftGroup++ pyramid + octree path, touching objects): every per-class
+    clustering call of the forward is compared with the oracle BFS on the same neighbour lists, bit for bit (lists cut by
+    the 1000 cap make directed edges into other components here -- the case that exposed the emit race of round 2)."""
+    from softgroup_b200.model import softgroup as sg
+    scan = synth.make_scan('c5_stpls3d', seed=0, n_points=1500000)
+    torch.manual_seed(0)
+    model = SoftGroup(**model_cfg('stpls3d++')).cuda().eval()
+    hb = harness.to_host_batch(scan, pin=False)
+    inj = harness.pointwise_injection(scan, sigma=0.3, seed=0)
+    orig = sg.bfs_cluster_segments
+    checked = []
+
+    def bfs(ni, sl, thr, **kw):
+        pidx, poff = orig(ni, sl, thr, **kw)
+        if len(checked) < 4 and not kw:  # the first four classes: ~50k nodes x ~1000 neighbours each
+            wi, wo = oracle.bfs_cluster(np.full(20, -1, np.float32), ni.cpu().numpy(), sl.cpu().numpy(), float(thr), 0)
+            assert np.array_equal(poff.cpu().numpy(), wo)
+            assert np.array_equal(pidx.cpu().numpy(), wi)
+            checked.append(int(poff.numel()) - 1)
+        return pidx, poff
+
+    monkeypatch.setattr(sg, 'bfs_cluster_segments', bfs)
+    with torch.no_grad():
+        ret = harness.run_scan(model, hb, device_only=True, inject_pointwise=inj)
+    assert len(checked) == 4 and sum(checked) > 50
+    n_prop = ret['proposals_offset'].numel() - 1
+    assert n_prop > 100
+    pidx = ret['proposals_idx']
+    assert int(pidx[:, 0].max()) == n_prop - 1 and int(pidx[:, 1].max()) < 1500000
+
+
+def test_full_size_s3dis_room_x4_split():
+    """BASELINE config 3 at FULL size (800k points, x4_split backbone): the forward finds the synthetic objects; every proposal
+    is one class segment's component (all its points pass that class's score threshold) and respects the size threshold."""
+    scan = synth.make_scan('c3_s3dis', seed=0, n_points=800000)
+    x4 = synth.to_x4_split(scan)
+    torch.manual_seed(0)
+    model = SoftGroup(**model_cfg('s3dis')).cuda().eval()
+    hb = harness.to_host_batch(x4, pin=False)
+    inj = harness.pointwise_injection(scan, sigma=0.03, seed=0)  # point order = order of the merged x4 outputs
+    with torch.no_grad():
+        ret = harness.run_scan(model, hb, device_only=True, inject_pointwise=inj)
+    off = ret['proposals_offset'].cpu().numpy()
+    pidx = ret['proposals_idx'].cpu().numpy()
+    assert len(off) - 1 > 50 and pidx.shape[0] > 400000
+    scores = inj[0].softmax(-1).cpu().numpy()
+    cnm = model.grouping_cfg['class_numpoint_mean']
+    for c in range(0, len(off) - 1, 7):
+        pts = pidx[off[c]:off[c + 1], 1]
+        assert np.all(pidx[off[c]:off[c + 1], 0] == c)
+        ok = (scores[pts] > 0.2).all(0)  # one class whose score passes on every point of the proposal
+        ok[:2] = False
+        assert ok.any()
+        assert len(pts) >= min(0.05 * cnm[k] for k in np.nonzero(ok)[0])

@@ -247,6 +247,40 @@ def test_bfs_cluster_capped_lists_and_chain():
     assert np.array_equal(ci.cpu().numpy(), oi)
 
 
+def test_bfs_cluster_edges_into_other_components():
+    """Directed edges INTO other components (a node of a later component lists nodes of earlier ones: what lists cut by the
+    1000 cap produce where objects touch). The listed node belongs to the component with the smaller seed and must not be
+    claimed by the later one, whichever of the two the GPU happens to emit first: many components in flight at once,
+    repeated to give the race a chance (it corrupted the BFS order on the 1.5M-point STPLS3D-shape tile before the fix)."""
+    rng = np.random.RandomState(17)
+    mean = np.full(20, -1, np.float32)
+    sizes = rng.randint(40, 400, 300)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    n = int(sizes.sum())
+    lists = []
+    for g, (s0, sz) in enumerate(zip(starts, sizes)):
+        for i in range(sz):
+            u = s0 + i
+            nb = [s0 + (i + 1) % sz, s0 + (i * 7 + 3) % sz]               # a cycle + a chord: the group is strongly connected
+            nb += list(s0 + rng.randint(0, sz, rng.randint(0, 6)))
+            if g > 0:                                                    # edges into EARLIER groups only (labels stay apart)
+                k = rng.randint(0, 12)
+                h = rng.randint(0, g, k)
+                nb += list(starts[h] + (rng.rand(k) * sizes[h]).astype(np.int64))
+            rng.shuffle(nb)
+            lists.append(np.asarray(nb, np.int32))
+    lens = np.array([len(x) for x in lists], np.int32)
+    idx = np.concatenate(lists).astype(np.int32)
+    sl = np.stack([np.concatenate([[0], np.cumsum(lens)[:-1]]), lens], 1).astype(np.int32)
+    oi, oo = oracle.bfs_cluster(mean, idx, sl, 10.0, 0)
+    assert len(oo) - 1 == len(sizes) and oi.shape[0] == n
+    d_idx, d_sl = _cuda(idx), _cuda(sl)
+    for rep in range(10):
+        ci, co = ops.bfs_cluster(torch.from_numpy(mean), d_idx, d_sl, 10.0, 0)
+        assert np.array_equal(co.cpu().numpy(), oo), rep
+        assert np.array_equal(ci.cpu().numpy(), oi), rep
+
+
 def test_bfs_cluster_full_size_pipeline():
     # full-size scan, one class at a time like the reference loop; GPU lists -> GPU bfs vs oracle bfs on same lists
     scan = synth.make_scan('c2_scannet', seed=1)
