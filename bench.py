@@ -414,10 +414,9 @@ def main():
 
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local_rank)
-    # The host side of a scan is launch latency, not throughput: keep torch's intra-op pool small (a 128-thread pool woken
-    # for tiny CPU ops cost 3 ms per scan end to end) and, with one rank per GPU, give every rank its own share of the cores
-    # of ITS GPU's NUMA node (NVML's ideal CPU affinity; the GPUs of the 8-GPU box sit four per node).
-    torch.set_num_threads(min(8, max(1, (os.cpu_count() or 8) // max(world, 1))))
+    # The host side of a scan is launch latency, not throughput: no intra-op pool and, with one rank per GPU, every rank on its
+    # own share of the cores of ITS GPU's NUMA node (NVML's ideal CPU affinity; the GPUs of the 8-GPU box sit four per node).
+    torch.set_num_threads(1)  # (1 / 8 / 128 threads measured the same on one GPU: GPU call 33; 1 keeps 8 ranks x 3 scan threads quiet)
     if world > 1:
         try:
             import pynvml
@@ -539,6 +538,8 @@ def main():
         model.use_plan = False
         timed(step_device, min(args.steps, 5), 1, instrument=True)
         model.use_plan = True
+    from softgroup_b200 import spconv as _spconv
+    _spconv.check_overflow()  # the device-resident legs keep the forward free of host waits: checked once here
     # launches counted over warmup+steps of the first leg -> per timed region
     launches_per_step = launches // (args.steps + max(args.warmup, 3))
 

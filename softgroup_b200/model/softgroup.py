@@ -290,8 +290,11 @@ class SoftGroup(nn.Module):
             ret.update(semantic_preds=semantic_preds, pt_offsets=pt_offsets)
         else:
             ret.update(fetch.finish())
-        if semantic_scores.is_cuda:
-            spconv.check_overflow()  # an activation beyond the fp16 hi/lo range raises here instead of saturating silently
+        if semantic_scores.is_cuda and not device_only:
+            # an activation beyond the fp16 hi/lo range raises here instead of saturating silently (the host has just waited
+            # for the results anyway). device_only callers keep the forward free of host waits and call
+            # spconv.check_overflow() themselves where they synchronise.
+            spconv.check_overflow()
         if self.profile_stages:
             torch.cuda.synchronize()
             self.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._events[:-1], self._events[1:])}

@@ -194,17 +194,32 @@ class Plan(object):
 
         opened = -1
         lib = _lib.lib()
+        ptrs[self.in_buf] = feats.data_ptr()
+        # the argument arrays live for the whole run and are updated in place when a level opens (they were rebuilt from
+        # Python lists for every segment: ~0.3 ms of host time per scan)
+        c_bufs = (ctypes.c_void_p * len(ptrs))()
+        c_subm, c_down, c_inv = (ctypes.c_void_p * L)(), (ctypes.c_void_p * L)(), (ctypes.c_void_p * L)()
+        c_M = (ctypes.c_int * L)()
+        c_bufs[self.in_buf] = ptrs[self.in_buf]
+        stream = core._stream()
+        op_size = ctypes.sizeof(UnetOp)
         for (i0, i1, need) in self.segments:
             while opened < need:
                 opened += 1
                 open_level(opened)
-            ptrs[self.in_buf] = feats.data_ptr()
-            c_bufs = (ctypes.c_void_p * len(ptrs))(*[p or None for p in ptrs])
-            mk = lambda lst: (ctypes.c_void_p * L)(*[(t.data_ptr() if t is not None else None) for t in lst])  # noqa: E731
-            c_M = (ctypes.c_int * L)(*M)
-            seg = ctypes.cast(ctypes.byref(self._c_ops, i0 * ctypes.sizeof(UnetOp)), ctypes.c_void_p)
+                k = opened
+                for b, _w in bufs_of_level[k]:
+                    c_bufs[b] = ptrs[b] or None
+                ptrs[self.in_buf] = feats.data_ptr()  # (open_level(0) gave the input buffer an arena slot: the caller's rows win)
+                c_bufs[self.in_buf] = ptrs[self.in_buf]
+                c_M[k] = M[k]
+                c_subm[k] = subm[k].data_ptr() if subm[k] is not None else None
+                if k > 0:
+                    c_down[k - 1] = down[k - 1].data_ptr() if down[k - 1] is not None else None
+                    c_inv[k - 1] = inv[k - 1].data_ptr() if inv[k - 1] is not None else None
+            seg = ctypes.cast(ctypes.byref(self._c_ops, i0 * op_size), ctypes.c_void_p)
             with profiler.record('unet_run', 0):
-                check(lib.sgb_unet_run(seg, i1 - i0, c_bufs, mk(subm), mk(down), mk(inv), c_M, L, core._stream()), 'sgb_unet_run')
+                check(lib.sgb_unet_run(seg, i1 - i0, c_bufs, c_subm, c_down, c_inv, c_M, L, stream), 'sgb_unet_run')
         o = self.out
         level, width = self.bufs[o.buf]
         base = ptrs[o.buf]

@@ -195,12 +195,15 @@ def _randomize_bn(model, seed):
                 m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
 
 
-@pytest.mark.parametrize('channels,num_blocks', [(16, 4), (32, 7)])
-def test_backbone_vs_oracle(channels, num_blocks):
-    """Whole sparse U-Net (53 SubM + 6 down + 6 inverse + 6 1x1 + 65 BN/ReLU at 32x7) vs the numpy restatement."""
+@pytest.mark.parametrize('channels,num_blocks,shape,n', [(16, 4, 'c1_plumbing', 6000), (32, 7, 'c1_plumbing', 6000),
+                                                         (32, 7, 'c2_scannet', 60000)])
+def test_backbone_vs_oracle(channels, num_blocks, shape, n):
+    """Whole sparse U-Net (53 SubM + 6 down + 6 inverse + 6 1x1 + 65 BN/ReLU at 32x7) vs the numpy restatement accumulating
+    in float64 -- also at 60 000 points of the ScanNet-shape room (~58k voxels: levels 0-3 run the persistent ring kernel,
+    the deep levels the split-K register-gather kernel, as in the bench)."""
     import oracle
     torch.manual_seed(0)
-    scan = synth.make_scan('c1_plumbing', seed=0, n_points=6000)
+    scan = synth.make_scan(shape, seed=0, n_points=n)
     vc, v2p, p2v = oracle.voxelization_idx(scan['coords'], 1, 4)
     feats = np.concatenate([scan['feats'], scan['coords_float']], 1).astype(np.float32)
     vfeats = oracle.voxelization(feats, p2v, 4)
