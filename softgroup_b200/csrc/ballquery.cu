@@ -334,27 +334,48 @@ __global__ void __launch_bounds__(BqCfg<PASS>::kThreads, BqCfg<PASS>::kPerSM) bq
       }
       }  // !ordered
       // ---- queries of this cell: one warp each ----------------------------------------------------
+      // The two loops below are 78 % of the kernel's 607 M warp instructions (ncu source page, round 2): they run on raw
+      // 32-bit shared-memory addresses (the generic-pointer form re-derived the shared window base in every iteration) and
+      // without a bounds test -- the staged stencil is padded to a multiple of 32 with records that can never hit (NaN).
+      const int total_pad = (total_s + 31) & ~31;
+      for (int t = total_s + tid; t < total_pad; t += kBqThreads)
+        S[t] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fffffff));
+      __syncthreads();
+      const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(S);
+      const uint32_t m_addr = (uint32_t)__cvta_generic_to_shared(bm + warp * (kBqSMax / 32));  // this warp's ballot masks
+      const unsigned lt_mask = (1u << lane) - 1u;
+      const int nblk = total_pad >> 5;
       for (int q = warp; q < q_cnt; q += kBqWarps) {
-        float4 qp = w.sorted[q_start + q];
-        int qi = __float_as_int(qp.w);
+        const float4 qp = w.sorted[q_start + q];
+        const int qi = __float_as_int(qp.w);
         // pass 1: count (first 1000 by index); pass 2: write straight to the reserved global range. The candidates
         // sit in shared memory, so scanning twice is cheaper than staging 4 KB per warp (which would cap the CTA at
-        // 8 warps and quadruple the per-cell sort time).
-        // the ballot masks of pass 1 are kept in the (now idle) bitmap area, one word per 32 candidates, so pass 2 does
-        // not recompute distances and only touches the index word of actual hits
-        uint32_t *masks = bm + warp * (kBqSMax / 32);
-        int cnt = 0, last = 0;
-        for (int b0 = 0; b0 < total_s && cnt < SGB_MAX_NEIGHBORS; b0 += 32) {
-          int t = b0 + lane;
-          bool hit = false;
-          if (t < total_s) {
-            float4 c = S[t];
-            hit = bq_hit(qp.x, qp.y, qp.z, c.x, c.y, c.z, r2);
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (lane == 0) masks[b0 >> 5] = m;
+        // 8 warps and quadruple the per-cell sort time). The ballot masks of pass 1 are kept in the (now idle) bitmap
+        // area, one word per 32 candidates, so pass 2 does not recompute distances and only touches the index word of
+        // actual hits.
+        int cnt = 0, nb = 0;
+        uint32_t ca = s_addr + (uint32_t)lane * 16u;
+        // two blocks of 32 candidates per trip (a block counted beyond the cap only leaves an unused mask behind: pass 2
+        // stops after `cnt` hits)
+        while (nb + 1 < nblk && cnt < SGB_MAX_NEIGHBORS) {
+          float ax, ay, az, aw, bx, by, bz, bw;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw) : "r"(ca));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bx), "=f"(by), "=f"(bz), "=f"(bw) : "r"(ca + 512u));
+          const unsigned m0 = __ballot_sync(0xffffffffu, bq_hit(qp.x, qp.y, qp.z, ax, ay, az, r2));
+          const unsigned m1 = __ballot_sync(0xffffffffu, bq_hit(qp.x, qp.y, qp.z, bx, by, bz, r2));
+          if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(m_addr + (uint32_t)nb * 4u), "r"(m0), "r"(m1) : "memory");
+          cnt = min(cnt + __popc(m0) + __popc(m1), SGB_MAX_NEIGHBORS);
+          nb += 2;
+          ca += 1024u;
+        }
+        while (nb < nblk && cnt < SGB_MAX_NEIGHBORS) {
+          float cx, cy, cz, cwv;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(cwv) : "r"(ca));
+          const unsigned m = __ballot_sync(0xffffffffu, bq_hit(qp.x, qp.y, qp.z, cx, cy, cz, r2));
+          if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(m_addr + (uint32_t)nb * 4u), "r"(m) : "memory");
           cnt = min(cnt + __popc(m), SGB_MAX_NEIGHBORS);
-          last = b0 + 32;
+          nb++;
+          ca += 512u;
         }
         __syncwarp();
         int base = 0;
@@ -364,15 +385,22 @@ __global__ void __launch_bounds__(BqCfg<PASS>::kThreads, BqCfg<PASS>::kPerSM) bq
           start_len[2 * (size_t)qi + 1] = cnt;
         }
         base = __shfl_sync(0xffffffffu, base, 0);
-        long long room = capacity - (long long)base;  // reference truncation (bfs_cluster.cu:55-61)
-        int cw = (room <= 0) ? 0 : (((long long)base + cnt >= capacity) ? (int)room : cnt);
+        const long long room = capacity - (long long)base;  // reference truncation (bfs_cluster.cu:55-61)
+        const int cw = (room <= 0) ? 0 : (((long long)base + cnt >= capacity) ? (int)room : cnt);
+        int32_t *__restrict__ out = idx + base;
         int done = 0;
-        for (int b0 = 0; b0 < last && done < cw; b0 += 32) {
-          const unsigned m = masks[b0 >> 5];
-          const bool hit = (m >> lane) & 1u;
-          int pos = done + __popc(m & ((1u << lane) - 1));
-          if (hit && pos < cw) idx[(size_t)base + pos] = __float_as_int(S[b0 + lane].w);
+        uint32_t wa = s_addr + (uint32_t)lane * 16u + 12u;  // the index word of this lane's candidate
+        for (int b = 0; b < nb && done < cw; b++) {
+          unsigned m;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(m_addr + (uint32_t)b * 4u));
+          const int pos = done + __popc(m & lt_mask);
+          if (((m >> lane) & 1u) && pos < cw) {
+            int id;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(id) : "r"(wa));
+            out[pos] = id;
+          }
           done += __popc(m);
+          wa += 512u;
         }
         __syncwarp();
       }
