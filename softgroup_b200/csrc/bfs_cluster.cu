@@ -31,7 +31,7 @@ struct BfsWs {
   int32_t *cid_of;     // [N] seed -> cluster id (kept) or -1
   int32_t *members;    // [N] nodes of kept clusters, grouped by cluster (unordered inside)
   int32_t *cursor;     // [N] per-cluster fill cursor / per-cluster level totals
-  int32_t *scalars;    // 0: changed flag, 1: max list length, 2..: spare
+  int32_t *scalars;    // [64] 0: changed flag, 1: max list length, 8..19: pass flags, 32..43: frontier queue lengths
   long long *totals;   // [1] packed total
   long long *scan_tmp;
 };
@@ -76,36 +76,64 @@ __device__ __forceinline__ unsigned long long ld_ca_u64(const unsigned long long
   return v;
 }
 
-// Label propagation, one warp per source node: the (pointer-chased) label of u is pushed to every listed v. A node
-// re-reads its list only when its chased label is lower than the one it pushed last time (`w.wins`, idle until the
-// emit phase, keeps the last pushed label): every pass chases every node's label (2-3 words per node) but the 4 bytes
-// per edge are read once per CHANGE of the source label instead of once per pass (measured round 2: 1.43 -> 0.86 ms of
-// labelling per 150k-point scan). The pass in which nobody pushes ends the iteration: then
-// label[v] <= pushed[u] <= label[u] for every edge u->v, which is the fixed point of the full iteration.
-// Passes are enqueued in batches without a host round trip: pass `it` raises flags[it] when it pushed anything and
-// returns at once when pass it-1 did not (the fixed point has been reached; the remaining launches of the batch are
-// empty). The host looks at the last flag of the batch at the sync it needs anyway for the cluster totals.
-__global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len,
-                                              int N, BfsWs w, int it, int cont, int32_t *__restrict__ flags) {
+// Label propagation (frontier iteration), two kernels per pass.
+//   select: one THREAD per node chases its label (pointer jumping: an ancestor's label is an ancestor too) and decides
+//           whether the node has something new to tell its out-neighbours -- its chased label is lower than the one it
+//           pushed last time (`w.wins`, idle until the emit phase, keeps the last pushed label). Such nodes go into a
+//           queue (node, label to push).
+//   push:   one WARP per queue entry pushes the label to every listed node (4 bytes per edge are read once per CHANGE of the
+//           source label instead of once per pass: 1.43 -> 0.86 ms per 150k-point scan, round 2).
+// Until GPU call 35 both steps ran in one kernel with a static node -> warp mapping; passes 2-3 of a 150k-point scan, where
+// 40 % resp. 2 % of the nodes are active, then took 325 + 233 us against 151 us for the pass that reads EVERY list
+// (ncu: long_scoreboard, a few warps with seven 1000-entry lists each while the others idle). Queue entries cost the same
+// (~1000 edges each), so a strided walk over the queue is balanced.
+// The pass in which nobody is selected ends the iteration: then label[v] <= pushed[u] <= label[u] for every edge u->v,
+// the fixed point of the full iteration. Passes are enqueued in batches without a host round trip: pass `it` raises
+// flags[it] when it selected anything and returns at once when pass it-1 did not. The queue lives in arrays the emit
+// phase owns later (members = node, cid_of = label); the entry count of pass `it` in scalars[32 + it].
+__global__ void bfs_frontier_select_kernel(int N, BfsWs w, int it, int cont, int32_t *__restrict__ flags) {
   if (it > 0 && *(volatile int32_t *)&flags[it - 1] == 0) return;
   const int first_pass = it == 0 && !cont;  // cont: a later batch continues the iteration (w.wins is valid)
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   volatile int32_t *label = w.label;
-  bool pushed_any = false;
-  for (int u = warp; u < N; u += nwarps) {
-    int lu = label[u];
-    while (true) {  // pointer jumping: an ancestor's label is an ancestor too
-      int l2 = label[lu];
+  bool active = false;
+  int lu = 0;
+  if (u < N) {
+    const int l0 = label[u];
+    lu = l0;
+    while (true) {
+      const int l2 = label[lu];
       if (l2 >= lu) break;
       lu = l2;
     }
-    if (lane == 0 && lu < label[u]) atomicMin(&w.label[u], lu);
+    if (lu < l0) atomicMin(&w.label[u], lu);
     const int prev = first_pass ? 0x7fffffff : *(volatile int32_t *)&w.wins[u];
-    if (lu >= prev) continue;  // warp-uniform: nothing new to tell the out-neighbours
-    pushed_any = true;
-    int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
+    active = lu < prev;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, active);
+  if (!m) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&w.scalars[32 + it], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (active) {
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    w.members[pos] = u;
+    w.cid_of[pos] = lu;
+    w.wins[u] = lu;  // what the push kernel of this pass tells the neighbours
+  }
+  if (lane == 0) flags[it] = 1;
+}
+
+__global__ void bfs_frontier_push_kernel(const int32_t *__restrict__ idxs, const int32_t *__restrict__ start_len, BfsWs w, int it,
+                                         const int32_t *__restrict__ flags) {
+  if (*(volatile const int32_t *)&flags[it] == 0) return;  // nothing selected in this pass (or the iteration ended earlier)
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int count = *(volatile int32_t *)&w.scalars[32 + it];
+  for (int e = warp; e < count; e += nwarps) {
+    const int u = w.members[e], lu = w.cid_of[e];
+    const int s = __ldg(&start_len[2 * (size_t)u]), l = __ldg(&start_len[2 * (size_t)u + 1]);
     // four independent (index, label) load pairs in flight per lane: the loop is latency bound (a list entry, then the
     // label it points to), not bandwidth bound
     for (int j0 = 0; j0 < l; j0 += 128) {
@@ -121,10 +149,7 @@ __global__ void bfs_propagate_frontier_kernel(const int32_t *__restrict__ idxs, 
       for (int t = 0; t < 4; t++)
         if (v[t] >= 0 && lv[t] > lu) atomicMin(&w.label[v[t]], lu);  // a stale (higher) value only costs a redundant atomic
     }
-    __syncwarp();
-    if (lane == 0) w.wins[u] = lu;
   }
-  if (pushed_any && lane == 0) flags[it] = 1;
 }
 
 __global__ void bfs_size_kernel(int N, const int32_t *__restrict__ start_len, BfsWs w) {
@@ -487,10 +512,13 @@ int sgb_bfs_cluster_count(const int32_t *d_ball_query_idxs, const int32_t *d_sta
   for (int batch = 0; batch < 100000; batch++) {
     if (batch > 0) {
       SGB_CUDA_CHECK(cudaMemsetAsync(flags, 0, kBatch * 4, st));
+      SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars + 32, 0, kBatch * 4, st));
       SGB_CUDA_CHECK(cudaMemsetAsync(w.size, 0, (size_t)N * 4, st));
     }
     for (int it = 0; it < kBatch; it++) {
-      bfs_propagate_frontier_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, N, w, it, batch > 0, flags);
+      bfs_frontier_select_kernel<<<nb, 256, 0, st>>>(N, w, it, batch > 0, flags);
+      SGB_LAUNCH_CHECK();
+      bfs_frontier_push_kernel<<<grid, 256, 0, st>>>(d_ball_query_idxs, d_start_len, w, it, flags);
       SGB_LAUNCH_CHECK();
     }
     bfs_size_kernel<<<nb, 256, 0, st>>>(N, d_start_len, w);

@@ -201,6 +201,39 @@ def test_frontier_label_iteration_reaches_reference_labels(seed):
     assert label == want
 
 
+@pytest.mark.parametrize('seed', range(6))
+def test_select_then_push_iteration_reaches_reference_labels(seed):
+    """The two-kernel form of a pass (bfs_frontier_select_kernel / bfs_frontier_push_kernel): ALL nodes chase their label and
+    decide first (the queue holds (node, label to push), `pushed` is updated at selection), then the queued entries push --
+    the labels the selection saw are one pass old. Same fixed point, in any order inside either step."""
+    rng = np.random.RandomState(100 + seed)
+    n = 300
+    pts = rng.rand(n, 2) * (1.0 if seed % 2 else 3.0)
+    d = ((pts[:, None] - pts[None]) ** 2).sum(-1)
+    cap = 6
+    lists = [list(np.nonzero(d[u] < 0.02)[0][:cap]) for u in range(n)]
+    want = _reference_seed_labels(lists)
+    label = list(range(n))
+    pushed = [2**31 - 1] * n
+    for _ in range(10 * n):
+        queue = []
+        for u in rng.permutation(n):  # select
+            lu = label[u]
+            while label[lu] < lu:
+                lu = label[lu]
+            label[u] = min(label[u], lu)
+            if lu < pushed[u]:
+                queue.append((u, lu))
+                pushed[u] = lu
+        if not queue:
+            break
+        for k in rng.permutation(len(queue)):  # push
+            u, lu = queue[k]
+            for v in lists[u]:
+                label[v] = min(label[v], lu)
+    assert label == want
+
+
 # ---- cooperative gather of spconv_tc_kernel<1> (round-2 candidate): index arithmetic emulated lane by lane --------
 def test_coop_gather_tile_indexing_is_a_conflict_free_transpose():
     """Write side: instruction j, lane l -> row R = 4j + (l >> 3), logical 16-byte chunk i = l & 7, physical chunk
