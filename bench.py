@@ -495,7 +495,9 @@ def main():
                 evs.append((e0, e1))
             barrier()
             wall = time.perf_counter() - t_wall
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        timed.last_per_step = per_step
+        ms = sum(per_step)
         return ms, wall, out
 
     pipe = harness.ScanPipeline(model, workers=args.inflight) if args.inflight > 1 else None
@@ -526,7 +528,9 @@ def main():
         l0 = _lib.lib().sgb_launch_count()
         seq_dev_ms, dev_wall, out = timed(step_device, args.steps, max(args.warmup, 3))
         launches = (_lib.lib().sgb_launch_count() - l0)
+        seq_dev_steps = sorted(timed.last_per_step)
         seq_e2e_ms, e2e_wall, ret = timed(lambda: harness.run_scan(model, hb, inject_pointwise=inj), args.steps, 3)
+        seq_e2e_steps = sorted(timed.last_per_step)
         if pipe is not None:
             dev_ms, dev_wall = timed_inflight(step_device, args.steps, max(args.warmup, 3))
             e2e_ms, e2e_wall = timed_inflight(lambda: harness.run_scan(model, hb, inject_pointwise=inj), args.steps, 3)
@@ -604,6 +608,11 @@ def main():
                     sequential=dict(note='one scan at a time (latency): device step with inputs resident / end to end from '
                                     'pinned host tensors', ms_per_step=seq_dev_ms_max / args.steps,
                                     e2e_ms_per_step=seq_e2e_ms_max / args.steps,
+                                    this_rank_ms_min_median_max=[round(seq_dev_steps[0], 3), round(seq_dev_steps[len(seq_dev_steps) // 2], 3),
+                                                                 round(seq_dev_steps[-1], 3)],
+                                    this_rank_e2e_ms_min_median_max=[round(seq_e2e_steps[0], 3),
+                                                                     round(seq_e2e_steps[len(seq_e2e_steps) // 2], 3),
+                                                                     round(seq_e2e_steps[-1], 3)],
                                     value=world * args.steps / (seq_dev_ms_max / 1e3),
                                     e2e_value=world * args.steps / (seq_e2e_ms_max / 1e3)),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
