@@ -11,6 +11,7 @@ per GPU per step (weak scaling, scans are independent; NCCL only reduces the tim
 Prints ONE JSON line (see the contract in the task description / DESIGN.md section "Measurement").
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -479,6 +480,11 @@ def main():
         with torch.no_grad():
             for _ in range(warmup):
                 fn()
+            # every object alive after the warm-up (model, plans, cached tensors) moves to the permanent generation: a full
+            # collection of Python's cyclic GC in the middle of a timed step cost 10-20 ms once per leg (one 23-31 ms step
+            # among 20 of 10.9 ms end to end, GPU call 40)
+            gc.collect()
+            gc.freeze()
             barrier()
             evs = []
             t_wall = time.perf_counter()
@@ -511,6 +517,8 @@ def main():
                 fn()      # would then pay a fresh cudaHostAlloc for its own
                 return None
             pipe.map(call, range(warmup))
+            gc.collect()
+            gc.freeze()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t_wall = time.perf_counter()
