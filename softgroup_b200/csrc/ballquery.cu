@@ -43,6 +43,7 @@ struct BqWs {
   int32_t *slot_cnt;         // [cap]
   int32_t *slot_start;       // [cap]
   int32_t *slot_fill;        // [cap]
+  int32_t *slot_lo, *slot_hi;  // [cap] smallest / largest point index of the cell (the id range of a stencil without a pass over it)
   int32_t *cell_slot;        // [n] cell id -> slot
   int32_t *cell_cnt;         // [n] -> scanned in place to starts
   int32_t *slot_of;          // [n]
@@ -65,6 +66,8 @@ static bool bq_carve(void *ws, size_t bytes, int n, BqWs &w) {
   w.slot_cnt = a.take<int32_t>(w.cap);
   w.slot_start = a.take<int32_t>(w.cap);
   w.slot_fill = a.take<int32_t>(w.cap);
+  w.slot_lo = a.take<int32_t>(w.cap);
+  w.slot_hi = a.take<int32_t>(w.cap);
   w.cell_slot = a.take<int32_t>((size_t)n + 1);
   w.cell_cnt = a.take<int32_t>((size_t)n + 1);
   w.slot_of = a.take<int32_t>((size_t)n + 1);
@@ -123,6 +126,8 @@ __global__ void bq_insert_kernel(const float *__restrict__ xyz, const int32_t *_
   }
   w.slot_of[i] = (int32_t)s;
   atomicAdd(&w.slot_cnt[s], 1);
+  atomicMin(&w.slot_lo[s], i);
+  atomicMax(&w.slot_hi[s], i);
 }
 
 __global__ void bq_cellcnt_kernel(int n, BqWs w) {
@@ -215,15 +220,20 @@ __global__ void __launch_bounds__(BqCfg<PASS>::kThreads, BqCfg<PASS>::kPerSM) bq
       int cx = (int)((ckey >> 36) & 0x3FFFF) + (tid % 3) - 1;
       int cy = (int)((ckey >> 18) & 0x3FFFF) + ((tid / 3) % 3) - 1;
       int cz = (int)(ckey & 0x3FFFF) + (tid / 9) - 1;
-      int st = 0, ct = 0;
+      int st = 0, ct = 0, lo = 0x7fffffff, hi = -1;
       if (cx >= 0 && cy >= 0 && cz >= 0 && cx < 2 * kCellBias && cy < 2 * kCellBias && cz < 2 * kCellBias) {
         unsigned long long key = ((unsigned long long)seg << 54) | ((unsigned long long)cx << 36) |
                                  ((unsigned long long)cy << 18) | (unsigned long long)cz;
         uint32_t s = hash_find(w.keys, w.cap - 1, key);
-        if (s != 0xFFFFFFFFu) { st = w.slot_start[s]; ct = w.slot_cnt[s]; }
+        if (s != 0xFFFFFFFFu) { st = w.slot_start[s]; ct = w.slot_cnt[s]; lo = w.slot_lo[s]; hi = w.slot_hi[s]; }
       }
       nb_start[tid] = st;
       nb_cnt[tid] = ct;
+      // id range of the whole stencil from the per-cell ranges kept by bq_insert_kernel (this used to be a pass over the
+      // stencil's records in global memory between two CTA barriers, for every work item)
+      lo = __reduce_min_sync(0x07ffffffu, lo);
+      hi = __reduce_max_sync(0x07ffffffu, hi);
+      if (tid == 0) { s_lo = lo; s_hi = hi; }
     }
     __syncthreads();
     if (tid == 0) {
@@ -244,23 +254,6 @@ __global__ void __launch_bounds__(BqCfg<PASS>::kThreads, BqCfg<PASS>::kPerSM) bq
       // ---- order the stencil by point index. Point indices are distinct, so the sorted position of a record is
       //      the number of stencil members with a smaller index: one bit per index in a shared-memory bitmap +
       //      prefix popcounts gives it in O(|S| + range/32) instead of an O(|S| log^2 |S|) bitonic sort.
-      if (tid == 0) { s_lo = 0x7fffffff; s_hi = -1; }
-      __syncthreads();
-      {
-        int lo = 0x7fffffff, hi = -1;
-        for (int k = 0; k < 27; k++) {
-          int c = nb_cnt[k], st = nb_start[k];
-          for (int t = tid; t < c; t += kBqThreads) {
-            int id = __float_as_int(__ldg(&reinterpret_cast<const float *>(w.sorted + st + t)[3]));
-            lo = min(lo, id);
-            hi = max(hi, id);
-          }
-        }
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        hi = __reduce_max_sync(0xffffffffu, hi);
-        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
-      }
-      __syncthreads();
       const int lo = s_lo;
       const int nwords = (s_hi - lo + 32) >> 5;
       bool ordered = false;
@@ -452,6 +445,8 @@ static int bq_launch(int n, long long capacity, float radius, const float *xyz, 
   SGB_CUDA_CHECK(cudaMemsetAsync(w.keys, 0xFF, (size_t)w.cap * 8, st));
   SGB_CUDA_CHECK(cudaMemsetAsync(w.slot_cnt, 0, (size_t)w.cap * 4, st));
   SGB_CUDA_CHECK(cudaMemsetAsync(w.slot_fill, 0, (size_t)w.cap * 4, st));
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.slot_lo, 0x7f, (size_t)w.cap * 4, st));  // 0x7f7f7f7f: above every point index
+  SGB_CUDA_CHECK(cudaMemsetAsync(w.slot_hi, 0xFF, (size_t)w.cap * 4, st));  // -1
   SGB_CUDA_CHECK(cudaMemsetAsync(w.scalars, 0, 64 * 4, st));
   double h = (double)radius * (1.0 + 1e-4);
   int nb = div_up(n, 256);
@@ -492,7 +487,7 @@ extern "C" {
 size_t sgb_ballquery_workspace_bytes(int n) {
   if (n < 0) n = 0;
   size_t cap = bq_cap(n);
-  size_t b = align_up(64 * 4) + align_up(cap * 8) + 3 * align_up(cap * 4) + 3 * align_up(((size_t)n + 1) * 4) +
+  size_t b = align_up(64 * 4) + align_up(cap * 8) + 5 * align_up(cap * 4) + 3 * align_up(((size_t)n + 1) * 4) +
              3 * align_up((2 * (size_t)n + 2) * 4) +
              align_up(((size_t)n + 1) * 16) + align_up(scan_temp_elems((size_t)n + 1) * 4);
   return b + 1024;
