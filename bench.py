@@ -478,8 +478,10 @@ def main():
 
     def timed(fn, steps, warmup, instrument=False):
         with torch.no_grad():
+            out = None
             for _ in range(warmup):
-                fn()
+                out = fn()  # (kept while the next call runs, like in the timed loop: the second set of pinned result buffers
+                            #  is then allocated here and not by a 25 ms cudaHostAlloc inside the second timed step)
             # every object alive after the warm-up (model, plans, cached tensors) moves to the permanent generation: a full
             # collection of Python's cyclic GC in the middle of a timed step cost 10-20 ms once per leg (one 23-31 ms step
             # among 20 of 10.9 ms end to end, GPU call 40)

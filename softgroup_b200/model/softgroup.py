@@ -22,7 +22,8 @@ import torch
 import torch.nn as nn
 
 from .. import spconv
-from ..ops import (ball_query, ballquery_batch_p_nosync, bfs_cluster_segments, global_avg_pool, group_entries, sec_max, sec_min,
+from ..ops import (ball_query, ballquery_batch_p_nosync, bfs_cluster_segments, gather_rows, global_avg_pool, group_entries, sec_max,
+                   sec_min,
                    voxelization,
                    voxelization_idx)
 from ..ops import instances as inst_ops
@@ -575,7 +576,8 @@ class SoftGroup(nn.Module):
         clusters_offset = clusters_offset.to(dev).contiguous()
         batch_idx = clusters_idx[:, 0].long()
         c_idxs = clusters_idx[:, 1].long()
-        feats = feats[c_idxs]
+        feats = gather_rows(feats, clusters_idx[:, 1]) if (feats.is_cuda and feats.dtype == torch.float32 and feats.size(1) % 4 == 0) \
+            else feats[c_idxs]
         coords = coords[c_idxs].contiguous()
         coords_min = sec_min(coords, clusters_offset)
         coords_max = sec_max(coords, clusters_offset)

@@ -163,6 +163,22 @@ def ballquery_batch_p_nosync(coords, batch_idxs, batch_offsets, radius):
     return idx, start_len, total
 
 
+def gather_rows(feats, idx):
+    """out[i] = feats[idx[i]] for float32 rows (`x[idx.long()]` of the reference at softgroup.py:374 and :672): float4 rows at
+    ~3 TB/s instead of torch's generic int64 gather (0.5 TB/s on 131k x 32 rows)."""
+    L = _lib.lib()
+    feats = feats.contiguous()
+    assert feats.dtype == torch.float32 and feats.dim() == 2 and feats.is_cuda
+    idx = idx.int().contiguous()
+    n, C = idx.numel(), feats.size(1)
+    out = torch.empty((n, C), dtype=torch.float32, device=feats.device)
+    if n == 0:
+        return out
+    with profiler.record('gather_rows', 4 * n + 4 * C * (feats.size(0) + n)):
+        check(L.sgb_gather_rows(ptr(feats), ptr(idx), ptr(out), n, C, _stream()), 'sgb_gather_rows')
+    return out
+
+
 def group_entries(scores, classes, score_thr, min_npoint, batch_idxs, batch_size, coords_float, pt_offsets):
     """All classes of the grouping loop (softgroup/model/softgroup.py:430-446) in one pass on the device: entries in
     class-major, ascending point order. scores: softmax scores [N, C]; classes: list of class ids (<= 32).
