@@ -9,7 +9,7 @@
 // results): pts[e] = point, seg[e] = rank(class) * B + batch[point], shifted[e] = coords[point] + offsets[point] (one fp32
 // add, like the reference), seg_offsets = exclusive scan of the entries per (class, batch item). The PyTorch formulation of
 // the same thing was ~30 small launches (index, compare, sum, nonzero, bincount, cumsum, gathers) with two host
-// synchronisations and two pageable H2D copies in the middle of the forward; this is 3 launches and none.
+// synchronisations and two pageable H2D copies in the middle of the forward; this is 4 launches and none.
 // Selection is a strict fp32 comparison on the caller's softmax scores: bit-exact by construction.
 #include <algorithm>
 
@@ -18,7 +18,7 @@
 namespace sgb {
 
 constexpr int GE_THREADS = 256;  // one point per thread
-constexpr int GE_MAXC = 32;      // classes per call (one ballot bit each is NOT needed; the limit is the shared counters)
+constexpr int GE_MAXC = 32;      // classes per call (one bit of a thread's selection mask each)
 
 struct GeArgs {
   const float *scores; int N, C;

@@ -3,9 +3,10 @@
 // Same arithmetic and data formats as spconv_tc.cu (packed fp16 hi/lo activation rows, error-compensated products
 // hi*hi + hi*lo + lo*hi accumulated in fp32 in tensor memory), different data movement. Measurements that
 // shaped it (profiles/r2_umma_rate2.txt, profiles/README.md round 2):
-//   * the tensor pipe needs N/2 cycles per M = 128, K = 16 instruction; the ~150 cycles per k-step of the register-gather
-//     kernel were the issuing thread's own scalar instruction stream, not the pipe -> the issue loop here is unrolled per
-//     stage (4 UTCHMMA + 1 commit) with descriptors advanced by adds;
+//   * the tensor pipe needs max(~48, N/2) cycles per M = 128, K = 16 instruction (r2_umma_rate3.txt: the minimum does not
+//     overlap across issuing warps or CTAs) and holds the issuing thread until it takes the instruction; what that thread
+//     does between stages leaves the pipe idle -> the issue loop is unrolled per stage (up to 8 UTCHMMA + 1 commit), with
+//     descriptors advanced by adds;
 //   * a gathered row slice held in registers gives a prefetch distance of one iteration (tcgen05.wait::st drains the
 //     thread's outstanding loads), so the register-gather kernel's iteration time was the L2 latency -> rows are copied
 //     with cp.async (16 B per lane, 8 lanes per 128-byte line, zero-fill for absent neighbours) straight into the
@@ -18,8 +19,11 @@
 // One CTA per SM (all 512 TMEM columns, ~200 KB of shared memory) walks work items (128 output rows x NT columns)
 // round-robin; accumulators are double-buffered in TMEM so the epilogue of item j overlaps the pipeline of item j+1, and
 // the rulebook slice of item j+1 is staged by its own warp while item j runs.
-// Warp roles (480 threads): 0-7 gather (warp w owns the iteration slots g with g % gw == w, gw = min(8, 2 S - 2)), 8 MMA issue, 9 weight loader (TMA bulk
-// copies), 10 rulebook loader, 11-14 epilogue (TMEM lane group = warp % 4).
+// Warp roles (480 threads): 0-7 gather (warp w owns the iteration slots g with g % gw == w, gw = min(8, 2 S - 2)), 8 MMA
+// issue, 9 weight loader (TMA bulk copies), 10 rulebook loader, 11-14 epilogue (TMEM lane group = warp % 4).
+// What bounds it now is the turnover of the ring (slot free -> 32 copies issued -> landed -> MMA -> commit, ~2 500 cycles for
+// 3-4 pair stages in 227 KB): tried without gain -- two MMA-issuing warps, the next pair's barrier wait between the two slots
+// of a pair, per-slot release of the ring (profiles/README.md, ROUND2_NOTES.md).
 #include <algorithm>
 #include <cstdlib>
 
