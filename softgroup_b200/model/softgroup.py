@@ -320,6 +320,19 @@ class SoftGroup(nn.Module):
             v += t._version
         return (v, ts[0].data_ptr() if ts else 0, len(ts))
 
+    def __getstate__(self):
+        # copy.deepcopy / pickling of the module: per-thread scratch, compiled plans (ctypes arrays, raw device pointers) and
+        # the cached tensor list are rebuilt on demand
+        d = self.__dict__.copy()
+        for k in ('_tls', '_plan_tensors', '_seg_thr_cache'):
+            d.pop(k, None)
+        d['_plans'] = {}
+        return d
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._tls = threading.local()
+
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop('_plan_tensors', None)
         self._plans = {}

@@ -53,3 +53,21 @@ def test_reference_class_on_our_shims_has_identical_state_dict():
     for k in a:
         assert a[k].shape == b[k].shape, k
     ours.load_state_dict(a)  # strict
+
+
+def test_model_survives_deepcopy_and_pickle():
+    """The per-thread scratch (threading.local) and the compiled plans (ctypes arrays, raw pointers) stay out of the module's
+    state: copy.deepcopy and torch.save(module) work and the copies rebuild them on demand."""
+    import copy
+    import io
+    from softgroup_b200.configs import model_cfg
+    from softgroup_b200.model import SoftGroup
+    m = SoftGroup(**model_cfg('scannet', channels=16, num_blocks=3))
+    m2 = copy.deepcopy(m)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    for c in (m2, m3):
+        assert c._plans == {} and hasattr(c, '_tls')
+        assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
