@@ -589,6 +589,16 @@ def main():
                 traffic_note = tj.get('note')
         except Exception:
             pass
+        for k, v in prof['by_kernel'].items():
+            v['frac_of_hbm_peak'] = round(v['gbs'] / hbm_peak, 4)
+        if args.workload == 'c2' and 'ballquery_batch_p' in prof['by_kernel']:
+            # the ball query is bound by instruction issue, not bytes: its floor from the committed ncu capture
+            # (8.2 M warp-level blocks of 32 exact distance tests per scan at >= 9 thread-instructions per test on 148 SMs x 128
+            # lanes at 1.965 GHz ~ 63 us; 416 M warp instructions executed at 57 % issue-slot utilisation)
+            bq = prof['by_kernel']['ballquery_batch_p']
+            bq['issue_floor_us'] = 63.0
+            bq['frac_of_issue_floor'] = round(63.0 / max(bq['ms_per_step'] * 1e3, 1e-9), 4)
+            bq['issue_floor_source'] = 'offline: profiles/r2_ncu_grouping_per_launch.tsv + the instruction count of the test loop'
         roofline = dict(bound='hbm', kernel=dom['name'], achieved=dom['gbs'], peak=hbm_peak, unit='GB/s',
                         frac=dom['gbs'] / hbm_peak, traffic=traffic, traffic_source=traffic_note, peak_source=peak_src,
                         launches_per_step=dom['launches_per_step'], avg_launch_us=dom['avg_us'],
