@@ -13,6 +13,7 @@ from softgroup_b200.configs import model_cfg  # noqa: E402
 from softgroup_b200.model import SoftGroup  # noqa: E402
 
 workers = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+E2E = len(sys.argv) > 2 and sys.argv[2] == 'e2e'  # pinned host batch -> result dict instead of device-resident inputs
 torch.set_num_threads(1)
 torch.manual_seed(0)
 model = SoftGroup(**model_cfg('scannet')).cuda().eval()
@@ -23,6 +24,9 @@ dev = harness.device_batch(hb)
 
 
 def step(_):
+    if E2E:
+        harness.run_scan(model, hb, inject_pointwise=inj)
+        return None
     vc, v2p, p2v = ops.voxelization_idx(dev['coords'], 1)
     d = {k: v for k, v in dev.items() if k not in ('coords', 'voxel_coords', 'v2p_map', 'p2v_map')}
     model.forward_test(device_only=True, inject_pointwise=inj, voxel_coords=vc, v2p_map=v2p, p2v_map=p2v, **d)
@@ -32,7 +36,7 @@ def step(_):
 with torch.no_grad():
     for _ in range(3):
         step(0)
-pipe = harness.ScanPipeline(model, workers=workers)
+pipe = harness.ScanPipeline(model, workers=workers, freeze_gc=True)
 pipe.map(step, range(2 * workers))
 torch.cuda.synchronize()
 N = 12
